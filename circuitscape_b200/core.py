@@ -1,0 +1,441 @@
+"""Drivers of the hot path on the CUDA solver -- the host-side mirror of
+src/core.jl (pairwise) and src/raster/advanced.jl:151-333 (advanced).
+
+Public names follow the reference:
+    get_solver(cfg)                         src/core.jl:74-94
+    single_ground_all_pairs(prob, flags, cfg)  src/core.jl:70-72  -> solve(...)
+    advanced_kernel(prob, flags, cfg)       src/raster/advanced.jl:151-271
+    multiple_solver(cfg, solver, a, s, g, f)   src/raster/advanced.jl:274-305
+`solve(prob, ::CUDASolver)` is the batched direct-style driver (src/core.jl:312-515)
+re-thought for a device-resident solver: the pair list of a component is handed to
+ONE `cs_b200_solve_pairs` call; voltages, node currents and the cumulative/max
+accumulation stay on the GPU and only resistances (plus whatever per-pair maps the
+flags ask for) come back.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import solver as S
+
+NODATA = -9999.0
+RESISTANCE_INVALID = -777.0   # src/consts.jl:45
+
+
+# ---------------------------------------------------------------------------
+# config / selection  (src/config.jl:68-73, src/consts.jl:12-15, src/core.jl:74-94)
+# ---------------------------------------------------------------------------
+def _parse_solver(s):
+    """Unknown names fall back to cg+amg in the reference; here the only product
+    solver is the CUDA one, so anything outside the CUDA table is refused loudly."""
+    if s in S.CUDAB200:
+        return "st_cuda"
+    raise ValueError(f"solver = {s!r} is not served by circuitscape_b200 "
+                     f"(use one of {S.CUDAB200}; cg+amg/cholmod stay in Circuitscape.jl)")
+
+
+def get_solver(cfg):
+    _parse_solver(cfg.get("solver", "cuda"))
+    return S.CUDASolver(
+        bs=int(cfg.get("cholmod_batch_size", "1000")),
+        precision=cfg.get("precision", "double"),
+        device=int(cfg.get("gpu_device", "0")),
+        rtol=float(cfg.get("gpu_rtol", "1e-6")),
+        precond=cfg.get("gpu_preconditioner", "jacobi"),
+    )
+
+
+def _flag(cfg, key, default="false"):
+    return cfg.get(key, default) in ("True", "true", "1")   # src/config.jl:55-57
+
+
+@dataclass
+class OutputFlags:
+    """src/out.jl:1-10."""
+    write_volt_maps: bool = False
+    write_cur_maps: bool = False
+    write_cum_cur_map_only: bool = False
+    write_max_cur_maps: bool = False
+    set_null_currents_to_nodata: bool = False
+    set_null_voltages_to_nodata: bool = False
+    compress_grids: bool = False
+    log_transform_maps: bool = False
+
+    @classmethod
+    def from_cfg(cls, cfg):
+        return cls(**{k: _flag(cfg, k) for k in cls.__dataclass_fields__})
+
+
+@dataclass
+class Flags:
+    """RasterFlags / NetworkFlags (src/raster/pairwise.jl:1-12, src/network/pairwise.jl:84-92)."""
+    is_raster: bool = True
+    is_advanced: bool = False
+    outputflags: OutputFlags = field(default_factory=OutputFlags)
+
+    @classmethod
+    def from_cfg(cls, cfg):
+        return cls(is_raster=cfg.get("data_type", "raster") in ("raster", "Raster"),
+                   is_advanced=cfg.get("scenario", "pairwise") in ("advanced", "Advanced"),
+                   outputflags=OutputFlags.from_cfg(cfg))
+
+
+@dataclass
+class GraphProblem:
+    """src/core.jl:10-22 (hbmeta dropped: file metadata is not on the path)."""
+    G: sp.csr_matrix
+    cc: list                      # list of 1-based node-id arrays
+    points: np.ndarray            # graph node per focal point (1-based, 0 = none)
+    user_points: np.ndarray       # user ids
+    exclude_pairs: set = field(default_factory=set)
+    nodemap: np.ndarray | None = None
+    polymap: np.ndarray | None = None
+    cellmap: np.ndarray | None = None
+    solver: S.CUDASolver = field(default_factory=S.CUDASolver)
+    coords: tuple | None = None   # network mode: (i, j) 1-based edge list (Cumulative.coords)
+
+
+@dataclass
+class PairwiseOutput:
+    resistances: np.ndarray
+    voltmaps: dict = field(default_factory=dict)
+    curmaps: dict = field(default_factory=dict)
+    branch: dict = field(default_factory=dict)
+    cum_curmap: np.ndarray | None = None
+    max_curmap: np.ndarray | None = None
+    cum_node: np.ndarray | None = None
+    cum_branch: np.ndarray | None = None
+    num_solves: int = 0
+    iterations: int = 0
+    stats: list = field(default_factory=list)
+
+
+# ---------------------------------------------------------------------------
+# pair enumeration  (src/core.jl:386-424, 537-603)
+# ---------------------------------------------------------------------------
+def component_pairs(points, user_points, exclude, comp, shortcut):
+    """For one component: unique focal nodes `csub` (in focal-point order), the
+    node pairs to solve with their focal-index fan-out, and the index pairs that
+    share a node (R = 0, smash_repeats!)."""
+    points = np.asarray(points)
+    member = np.isin(points, comp) & (points != 0)
+    idx_by_node = {}
+    for k in np.nonzero(member)[0]:
+        idx_by_node.setdefault(int(points[k]), []).append(int(k))
+    csub = list(idx_by_node)
+    zero, solves = [], []
+    for pi, s in enumerate(csub[: (1 if shortcut else len(csub))]):
+        si = idx_by_node[s]
+        zero += [(si[a], si[b]) for a in range(len(si)) for b in range(a + 1, len(si))]
+        for d in csub[pi + 1:]:
+            fan = [(ci, cj) for ci in si for cj in idx_by_node[d]
+                   if (int(user_points[ci]), int(user_points[cj])) not in exclude]
+            if fan:
+                solves.append((s, d, fan))
+    return csub, solves, zero
+
+
+def construct_local_node_map(nodemap, comp, polymap):
+    """src/utils.jl:10-30: cell -> row of the component's matrix (1-based, 0 = none)."""
+    from .graph import construct_node_map
+    inside = np.isin(nodemap, comp)
+    local = np.where(inside, nodemap, 0)
+    if np.array_equal(local, nodemap):
+        return local
+    if polymap is None or np.size(polymap) == 0:
+        flat = local.reshape(-1, order="F")
+        nz = flat != 0
+        flat = flat.copy()
+        flat[nz] = np.arange(1, int(nz.sum()) + 1)
+        return flat.reshape(local.shape, order="F")
+    return construct_node_map(local, np.where(inside, polymap, 0))
+
+
+def _scatter(values, local_nodemap):
+    out = np.zeros(local_nodemap.shape, dtype=np.float64)
+    nz = local_nodemap != 0
+    out[nz] = values[local_nodemap[nz] - 1]
+    return out
+
+
+def _process_grid(cmap, cellmap, log_transform, set_null_to_nodata):
+    """src/out.jl:305-319."""
+    if log_transform:
+        pos = cmap > 0
+        cmap = np.where(pos, np.log10(np.where(pos, cmap, 1.0)), NODATA)
+    if set_null_to_nodata:
+        cmap = np.where(cellmap == 0, NODATA, cmap)
+    return cmap
+
+
+# ---------------------------------------------------------------------------
+# pairwise driver
+# ---------------------------------------------------------------------------
+def single_ground_all_pairs(prob: GraphProblem, flags: Flags, cfg=None, log=True) -> PairwiseOutput:
+    """src/core.jl:70-72."""
+    return solve(prob, prob.solver, flags, cfg, log)
+
+
+def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=True) -> PairwiseOutput:
+    o = flags.outputflags
+    P = len(prob.points)
+    R = -np.ones((P, P))
+    want_maps = o.write_volt_maps or o.write_cur_maps or o.write_cum_cur_map_only or o.write_max_cur_maps
+    shortcut = flags.is_raster and not want_maps and not prob.exclude_pairs      # src/core.jl:356-364
+    voltmatrix = np.zeros((P, P))
+    shortcut_res = -np.ones((P, P))
+    out = PairwiseOutput(resistances=None)
+    raster = flags.is_raster
+    if raster:
+        out.cum_curmap = np.zeros(prob.cellmap.shape)
+        out.max_curmap = np.full(prob.cellmap.shape, NODATA) if o.write_max_cur_maps else None
+    else:
+        out.cum_node = np.zeros(prob.G.shape[0])
+        out.cum_branch = np.zeros(len(prob.coords[0]))
+    G = sp.csr_matrix(prob.G)
+    points = np.asarray(prob.points)
+    ids = np.asarray(prob.user_points)
+
+    for comp in prob.cc:
+        comp = np.asarray(comp)
+        csub, solves, zero = component_pairs(points, ids, prob.exclude_pairs, comp, shortcut)
+        if not csub:
+            continue
+        for a, b in zero:
+            R[a, b] = R[b, a] = 0.0
+        if not solves:
+            continue
+        rows = comp - 1
+        matrix = G[rows][:, rows].tocsr()
+        local_of = np.zeros(G.shape[0] + 1, dtype=np.int64)
+        local_of[comp] = np.arange(len(comp))
+        src = np.array([local_of[s] for s, _, _ in solves])
+        dst = np.array([local_of[d] for _, d, _ in solves])
+        weight = np.array([len(f) for _, _, f in solves], dtype=np.float64)
+        need_curr = not shortcut                       # postprocess always builds the current map
+        per_pair_volt = o.write_volt_maps or shortcut or (not raster and not shortcut)
+        per_pair_curr = need_curr and ((o.write_cur_maps and not o.write_cum_cur_map_only) or not raster)
+        local_nodemap = construct_local_node_map(prob.nodemap, comp, prob.polymap) if raster and not shortcut else None
+        with S.construct_cholesky_factor(matrix, solver, log_transform=o.log_transform_maps) as factor:
+            bs = max(1, int(solver.bs))
+            for st in range(0, len(solves), bs):                                # src/core.jl:448-452
+                sl = slice(st, min(st + bs, len(solves)))
+                res = factor.solve_pairs(src[sl], dst[sl], weight[sl], want_volt=per_pair_volt,
+                                         want_curr=per_pair_curr, accumulate=need_curr)
+                out.stats.append(factor.stats())
+                out.num_solves += len(res["R"])
+                out.iterations += int(res["iters"].sum())
+                for col, (s, d, fan) in enumerate(solves[sl]):
+                    r = float(res["R"][col])
+                    v = res["volt"][:, col].astype(np.float64) if res["volt"] is not None else None
+                    cur = res["curr"][:, col].astype(np.float64) if res["curr"] is not None else None
+                    for ci, cj in fan:
+                        R[ci, cj] = R[cj, ci] = r
+                        key = (int(ids[ci]), int(ids[cj]))
+                        if shortcut:                                             # src/core.jl:685-703
+                            inside = np.nonzero(np.isin(points, comp) & (points != 0))[0]
+                            for i in inside[inside >= 1]:
+                                voltmatrix[i, cj] = 1.0 - v[local_of[points[i]]] / r
+                            continue
+                        if raster:
+                            if o.write_volt_maps:
+                                out.voltmaps[key] = _process_grid(_scatter(v, local_nodemap), prob.cellmap,
+                                                                  False, o.set_null_voltages_to_nodata)
+                            if per_pair_curr:
+                                out.curmaps[key] = _process_grid(_scatter(cur, local_nodemap), prob.cellmap,
+                                                                 o.log_transform_maps,
+                                                                 o.set_null_currents_to_nodata)
+                        else:
+                            out.voltmaps[key] = (comp, v)
+                            out.curmaps[key] = (comp, cur)
+                            out.branch[key] = _branch_currents(matrix, v, comp)
+            if need_curr:
+                cum, mx = factor.read_currents(want_max=True)
+                if raster:
+                    npost = float(weight.sum())
+                    cmap = _scatter(cum.astype(np.float64), local_nodemap)
+                    if o.log_transform_maps:
+                        # cells outside the component hold 0 -> log-transformed to NODATA per pair
+                        cmap = np.where(local_nodemap == 0, NODATA * npost, cmap)
+                    if o.set_null_currents_to_nodata:
+                        cmap = np.where(prob.cellmap == 0, NODATA * npost, cmap)
+                    out.cum_curmap += cmap
+                    if out.max_curmap is not None:
+                        mmap = _scatter(mx.astype(np.float64), local_nodemap)
+                        off = local_nodemap == 0
+                        mmap = np.where(off, NODATA if o.log_transform_maps else 0.0, mmap)
+                        if o.set_null_currents_to_nodata:
+                            mmap = np.where(prob.cellmap == 0, NODATA, mmap)
+                        out.max_curmap = np.maximum(out.max_curmap, mmap)
+                else:
+                    out.cum_node[rows] += cum
+                    _accumulate_branches(out, prob.coords)
+        if shortcut:
+            anchor = int(np.nonzero(points == csub[0])[0][0])
+            _update_shortcut_resistances(anchor, voltmatrix, shortcut_res, R, points, comp)
+    if shortcut:
+        R = shortcut_res
+    np.fill_diagonal(R, 0.0)
+    full = np.zeros((P + 1, P + 1))
+    full[0, 1:] = ids
+    full[1:, 0] = ids
+    full[1:, 1:] = R
+    out.resistances = full                                                      # src/core.jl:294-299
+    if raster:
+        out.cum_curmap = np.where(out.cum_curmap < NODATA, NODATA, out.cum_curmap)   # src/utils.jl:114-120
+        if out.max_curmap is not None:
+            out.max_curmap = np.where(out.max_curmap < NODATA, NODATA, out.max_curmap)
+    return out
+
+
+def _branch_currents(matrix, v, comp):
+    """Network mode branch currents |G_ij| |v_i - v_j| over the stored upper triangle
+    with the 1e-8 relative zeroing (src/out.jl:154-158, 250-290); host side, network
+    graphs only."""
+    coo = sp.triu(sp.csr_matrix(matrix), k=1).tocoo()
+    b = np.abs(coo.data) * (v[coo.row] - v[coo.col])
+    if len(b):
+        mx = b.max()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            b = np.where(np.abs(b / mx) < 1e-8, 0.0, b)
+    return comp[coo.row], comp[coo.col], np.abs(b)
+
+
+def _accumulate_branches(out, coords):
+    pos = {}
+    for k, (a, b) in enumerate(zip(coords[0], coords[1])):
+        pos.setdefault((int(a), int(b)), k)
+    out.cum_branch[:] = 0.0
+    for (gr, gc, val) in out.branch.values():
+        for a, b, x in zip(gr, gc, val):
+            k = pos.get((int(a), int(b)))
+            if k is None:
+                k = pos.get((int(b), int(a)))
+            out.cum_branch[k] += x
+
+
+def _update_shortcut_resistances(anchor, voltmatrix, shortcut, resistances, points, comp):
+    """src/core.jl:706-739:  R_2x = 2 R_12 V_x2 + R_1x - R_12."""
+    check = np.isin(points, comp) & (np.asarray(points) != 0)
+    l = resistances.shape[0]
+    for px in np.nonzero(check)[0]:
+        R1x = resistances[anchor, px]
+        if R1x == -1:
+            continue
+        shortcut[px, anchor] = shortcut[anchor, px] = R1x
+        for p2 in range(px, l):
+            if not check[p2]:
+                continue
+            R12 = resistances[anchor, p2]
+            if R12 == -1:
+                continue
+            if R1x != RESISTANCE_INVALID:
+                shortcut[anchor, p2] = shortcut[p2, anchor] = R12
+                R2x = 2 * R12 * voltmatrix[px, p2] + R1x - R12
+                if shortcut[p2, px] != RESISTANCE_INVALID:
+                    shortcut[p2, px] = shortcut[px, p2] = R2x
+            else:
+                shortcut[px, :] = RESISTANCE_INVALID
+                shortcut[:, px] = RESISTANCE_INVALID
+
+
+def compute_3col(r):
+    """src/out.jl:12-26."""
+    fp = r[1:, 0]
+    i, j = np.triu_indices(len(fp), k=1)
+    return np.column_stack([fp[i], fp[j], r[j + 1, i + 1]])
+
+
+# ---------------------------------------------------------------------------
+# advanced mode  (src/raster/advanced.jl:151-333)
+# ---------------------------------------------------------------------------
+@dataclass
+class AdvancedProblem:
+    """src/raster/advanced.jl:1-15."""
+    G: sp.csr_matrix
+    cc: list
+    sources: np.ndarray
+    grounds: np.ndarray
+    finitegrounds: np.ndarray       # [-9999.] sentinel when there are none
+    nodemap: np.ndarray | None = None
+    polymap: np.ndarray | None = None
+    cellmap: np.ndarray | None = None
+    solver: S.CUDASolver = field(default_factory=S.CUDASolver)
+
+
+@dataclass
+class AdvancedOutput:
+    voltages: np.ndarray
+    voltmap: np.ndarray | None = None
+    curmap: np.ndarray | None = None
+    node_currents: np.ndarray | None = None
+    branch: tuple | None = None
+
+
+def multiple_solver(cfg, solver, a, sources, grounds, finitegrounds):
+    """src/raster/advanced.jl:274-305: diag += finite grounds; rows/cols of Inf
+    grounds deleted (0 V); `multiple_solve`; zeros re-inserted."""
+    a = sp.csr_matrix(a, dtype=np.float64)
+    n = a.shape[0]
+    if finitegrounds[0] != NODATA:
+        a = (a + sp.diags(finitegrounds)).tocsr()
+    keep = np.nonzero(~(grounds == np.inf))[0]
+    asolve = a[keep][:, keep].tocsr()
+    volt = S.multiple_solve(solver, asolve, np.asarray(sources, dtype=np.float64)[keep])
+    v = np.zeros(n)
+    v[keep] = volt
+    return v
+
+
+def node_currents_host(G, v, finitegrounds=None):
+    """src/out.jl:178-207 on the host (advanced mode solves once per component; the
+    pairwise path uses the device kernel instead)."""
+    coo = sp.triu(sp.csr_matrix(G), k=1).tocoo()
+    n = G.shape[0]
+    d = np.abs(coo.data) * (v[coo.row] - v[coo.col])
+
+    def one(b):
+        if len(b):
+            mx = b.max()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                b = np.where(np.abs(b / mx) < 1e-8, 0.0, b)
+        s = np.zeros(n)
+        np.add.at(s, coo.col, np.maximum(b, 0.0))
+        np.add.at(s, coo.row, np.maximum(-b, 0.0))
+        return s
+
+    p, q = one(d), one(-d)
+    if finitegrounds is not None and finitegrounds[0] != NODATA:
+        fg = finitegrounds * v
+        p = p + np.where(fg < 0, -fg, 0.0)
+        q = q + np.where(fg > 0, fg, 0.0)
+    return np.where(p > q, p, q)
+
+
+def advanced_kernel(prob: AdvancedProblem, flags: Flags, cfg=None) -> AdvancedOutput:
+    G = sp.csr_matrix(prob.G)
+    n = G.shape[0]
+    raster = flags.is_raster
+    voltages = np.zeros(n)
+    outvolt = np.zeros(prob.nodemap.shape) if raster else None
+    outcurr = np.zeros(prob.nodemap.shape) if raster else None
+    for c in prob.cc:
+        rows = np.asarray(c) - 1
+        s_local, g_local = prob.sources[rows].copy(), prob.grounds[rows].copy()
+        if s_local.sum() == 0 or g_local.sum() == 0:                          # :194-196
+            continue
+        f_local = prob.finitegrounds[rows] if prob.finitegrounds[0] != NODATA else prob.finitegrounds
+        a_local = G[rows][:, rows].tocsr()
+        voltages[rows] += multiple_solver(cfg, prob.solver, a_local, s_local, g_local, f_local)
+        if raster:
+            lm = construct_local_node_map(prob.nodemap, np.asarray(c), prob.polymap)
+            outvolt += _scatter(voltages[rows], lm)
+            outcurr += _scatter(node_currents_host(a_local, voltages[rows], f_local), lm)
+    res = AdvancedOutput(voltages, outvolt, outcurr)
+    if not raster:
+        res.node_currents = node_currents_host(G, voltages, prob.finitegrounds)
+        res.branch = _branch_currents(G, voltages, np.arange(1, n + 1))
+    return res

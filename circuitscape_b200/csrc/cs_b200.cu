@@ -1,0 +1,799 @@
+// cs_b200.cu -- host side of libcsb200.so (C ABI in include/cs_b200.h).
+// Plain CUDA runtime, no torch.  One handle = one connected component's operator
+// resident on one B200 + a panel workspace for the batched PCG.
+#include "../../include/cs_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace csb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct GraphSlot {
+  cudaGraphExec_t exec = nullptr;
+  int chunk = 0;
+};
+
+}  // namespace
+
+struct cs_b200_handle {
+  int device = 0;
+  int dtype = CS_B200_F64;
+  int64_t n = 0, n_pad = 0, nnz = 0;
+  int* d_rowptr = nullptr;
+  int* d_colidx = nullptr;
+  void* d_vals = nullptr;
+  bool owns_matrix = true;
+  void* d_dinv = nullptr;
+  int* d_bstart = nullptr;
+  int nblocks = 0;
+  int ktmax = 8;
+  void *X = nullptr, *R = nullptr, *P = nullptr, *AP = nullptr, *B = nullptr, *stage = nullptr;
+  void *d_cum = nullptr, *d_max = nullptr;
+  PanelCtl* d_ctl = nullptr;
+  PanelCtl* h_ctl = nullptr;  // pinned
+  double* d_partials = nullptr;
+  float* d_flush = nullptr;
+  size_t flush_elems = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  int num_sms = 148;
+  int grid_spmm = 148, grid_ew = 148;
+  cs_b200_opts opts{};
+  cs_b200_stats stats{};
+  GraphSlot graphs[4];  // KT = 1,2,4,8
+  // optional per-launch SpMM timing (cs_b200_profile_spmm): event pairs harvested at
+  // every host poll, so the pool only has to cover one chunk of iterations.
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  double prof_ms = 0.0;
+  int64_t prof_launches = 0;
+  std::string err;
+  size_t esize() const { return dtype == CS_B200_F64 ? 8 : 4; }
+};
+
+namespace {
+
+int set_err(cs_b200_handle* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                      \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return set_err(h, CS_B200_ERR_CUDA, "CUDA error %s at %s:%d (%s)",                 \
+                     cudaGetErrorString(_e), __FILE__, __LINE__, #call);                 \
+  } while (0)
+
+int kt_index(int kt) { return kt == 1 ? 0 : kt == 2 ? 1 : kt == 4 ? 2 : 3; }
+
+// greedy row blocks: <= NNZ_CAP nnz and <= NT rows; an over-long row stands alone.
+void build_row_blocks(const std::vector<int>& rowptr, int64_t n, std::vector<int>& bstart) {
+  bstart.clear();
+  bstart.push_back(0);
+  int64_t r = 0;
+  while (r < n) {
+    int64_t r1 = r + 1;
+    const int64_t base = rowptr[r];
+    while (r1 < n && (r1 - r) < NT && (int64_t)rowptr[r1 + 1] - base <= NNZ_CAP) ++r1;
+    bstart.push_back((int)r1);
+    r = r1;
+  }
+}
+
+template <typename T>
+int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr) {
+  std::vector<int> bstart;
+  build_row_blocks(h_rowptr, h->n, bstart);
+  h->nblocks = (int)bstart.size() - 1;
+  CK(h, cudaMalloc(&h->d_bstart, bstart.size() * sizeof(int)));
+  CK(h, cudaMemcpyAsync(h->d_bstart, bstart.data(), bstart.size() * sizeof(int),
+                        cudaMemcpyHostToDevice, h->stream));
+  const size_t pe = (size_t)h->n_pad * h->ktmax;
+  void** bufs[] = {&h->X, &h->R, &h->P, &h->AP, &h->B, &h->stage};
+  for (void** b : bufs) {
+    CK(h, cudaMalloc(b, pe * sizeof(T)));
+    CK(h, cudaMemsetAsync(*b, 0, pe * sizeof(T), h->stream));
+  }
+  CK(h, cudaMalloc(&h->d_dinv, (size_t)h->n_pad * sizeof(T)));
+  CK(h, cudaMalloc(&h->d_cum, (size_t)h->n_pad * sizeof(T)));
+  CK(h, cudaMalloc(&h->d_max, (size_t)h->n_pad * sizeof(T)));
+  CK(h, cudaMalloc(&h->d_ctl, sizeof(PanelCtl)));
+  CK(h, cudaMemsetAsync(h->d_ctl, 0, sizeof(PanelCtl), h->stream));
+  CK(h, cudaMallocHost(&h->h_ctl, sizeof(PanelCtl)));
+  const int maxgrid = h->num_sms * 8;
+  CK(h, cudaMalloc(&h->d_partials, (size_t)maxgrid * 2 * MAXKT * sizeof(double)));
+  k_dinv<T><<<std::min<int64_t>((h->n_pad + 255) / 256, 4096), 256, 0, h->stream>>>(
+      (int)h->n, (int)h->n_pad, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (T*)h->d_dinv);
+  CK(h, cudaGetLastError());
+  CK(h, cudaStreamSynchronize(h->stream));
+  return cs_b200_reset_currents(h);
+}
+
+int common_create(cs_b200_handle* h, const cs_b200_opts* opts) {
+  if (opts) h->opts = *opts;
+  if (h->opts.panel_width == 0) h->opts.panel_width = 8;
+  if (h->opts.check_every <= 0) h->opts.check_every = 16;
+  if (h->opts.resid_gate <= 0) h->opts.resid_gate = 1e-4;
+  if (h->opts.use_graph == 0) h->opts.use_graph = 1;  // 0 -> default on; pass -1 to disable
+  const int pw = h->opts.panel_width;
+  if (pw != 1 && pw != 2 && pw != 4 && pw != 8)
+    return set_err(h, CS_B200_ERR_ARG, "panel_width must be 1, 2, 4 or 8 (got %d)", pw);
+  h->ktmax = pw;
+  if (h->opts.precond != CS_B200_PRECOND_JACOBI)
+    return set_err(h, CS_B200_ERR_UNSUPPORTED, "preconditioner %d not available in this build",
+                   h->opts.precond);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return set_err(h, CS_B200_ERR_CUDA,
+                   "no CUDA device available (%s): libcsb200 has no CPU fallback",
+                   cudaGetErrorString(e));
+  if (h->device < 0 || h->device >= ndev)
+    return set_err(h, CS_B200_ERR_ARG, "device %d out of range (0..%d)", h->device, ndev - 1);
+  CK(h, cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CK(h, cudaGetDeviceProperties(&prop, h->device));
+  h->num_sms = prop.multiProcessorCount;
+  h->grid_spmm = h->num_sms * 4;
+  h->grid_ew = h->num_sms * 4;
+  CK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(h, cudaEventCreate(&h->ev0));
+  CK(h, cudaEventCreate(&h->ev1));
+  CK(h, cudaEventCreate(&h->ev2));
+  CK(h, cudaEventCreate(&h->ev3));
+  h->n_pad = (h->n + 3) / 4 * 4;
+  return CS_B200_OK;
+}
+
+template <typename I>
+void narrow_indices(const I* src, int64_t count, int base, std::vector<int>& dst) {
+  dst.resize(count);
+  for (int64_t i = 0; i < count; ++i) dst[i] = (int)(src[i] - base);
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers (all on h->stream)
+// ---------------------------------------------------------------------------
+template <typename T, int KT, int MODE>
+void launch_spmm(cs_b200_handle* h, const T* X, T* Y, const T* B) {
+  const int grid = std::min(h->grid_spmm, h->nblocks);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profile) {
+    if (h->prof_used + 2 > h->prof_ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_ev.push_back(e); }
+    }
+    e0 = h->prof_ev[h->prof_used++];
+    e1 = h->prof_ev[h->prof_used++];
+    cudaEventRecord(e0, h->stream);
+  }
+  k_spmm<T, KT, MODE><<<grid, NT, 0, h->stream>>>(h->d_rowptr, h->d_colidx, (const T*)h->d_vals,
+                                                  h->d_bstart, h->nblocks, X, Y, B, h->d_ctl,
+                                                  h->d_partials);
+  if (h->profile) cudaEventRecord(e1, h->stream);
+  h->stats.kernel_launches++;
+  h->stats.spmm_launches++;
+}
+
+// after a stream sync: fold the recorded SpMM event pairs into the profile totals
+void harvest_profile(cs_b200_handle* h) {
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) {
+      h->prof_ms += ms;
+      h->prof_launches++;
+    }
+  }
+  h->prof_used = 0;
+}
+
+template <typename T, int KT>
+int ew_grid(cs_b200_handle* h) {
+  const size_t nelem = (size_t)h->n_pad * KT;
+  const size_t per = (size_t)NT * Vec<T>::N;
+  return (int)std::min<size_t>(h->grid_ew, (nelem + per - 1) / per);
+}
+
+template <typename T, int KT>
+void launch_iteration(cs_b200_handle* h) {
+  const size_t nelem = (size_t)h->n_pad * KT;
+  const int g = ew_grid<T, KT>(h);
+  launch_spmm<T, KT, 1>(h, (const T*)h->P, (T*)h->AP, nullptr);
+  k_cg_update_r<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->AP, (const T*)h->d_dinv,
+                                                (T*)h->R, h->d_ctl, h->d_partials);
+  k_cg_update_xp<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->R, (const T*)h->d_dinv,
+                                                 (T*)h->X, (T*)h->P, h->d_ctl);
+  h->stats.kernel_launches += 2;
+}
+
+template <typename T, int KT>
+int run_chunk(cs_b200_handle* h, int chunk) {
+  GraphSlot& gs = h->graphs[kt_index(KT)];
+  if (h->opts.use_graph > 0 && !h->profile) {
+    if (!gs.exec || gs.chunk != chunk) {
+      if (gs.exec) cudaGraphExecDestroy(gs.exec);
+      gs.exec = nullptr;
+      cudaGraph_t graph;
+      const int64_t kl = h->stats.kernel_launches, sl = h->stats.spmm_launches;
+      CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      for (int i = 0; i < chunk; ++i) launch_iteration<T, KT>(h);
+      CK(h, cudaStreamEndCapture(h->stream, &graph));
+      h->stats.kernel_launches = kl;
+      h->stats.spmm_launches = sl;
+      CK(h, cudaGraphInstantiate(&gs.exec, graph, 0));
+      cudaGraphDestroy(graph);
+      gs.chunk = chunk;
+    }
+    CK(h, cudaGraphLaunch(gs.exec, h->stream));
+    h->stats.kernel_launches += 3 * (int64_t)chunk;
+    h->stats.spmm_launches += chunk;
+  } else {
+    for (int i = 0; i < chunk; ++i) launch_iteration<T, KT>(h);
+    CK(h, cudaGetLastError());
+  }
+  return CS_B200_OK;
+}
+
+// Solve A X = B for the panel whose B is already staged and whose ctl (src/dst/weight)
+// has been uploaded.  Leaves X = solution, AP = B - A X, ctl (host copy) updated.
+template <typename T, int KT>
+int solve_panel(cs_b200_handle* h, double rtol, int64_t itmax) {
+  const size_t nelem = (size_t)h->n_pad * KT;
+  const double atol = h->opts.atol > 0 ? h->opts.atol
+                      : h->opts.atol < 0 ? 0.0
+                      : std::sqrt((double)std::numeric_limits<T>::epsilon());
+  const int g = ew_grid<T, KT>(h);
+  const int imax = (int)std::min<int64_t>(itmax, std::numeric_limits<int>::max() - 1);
+  CK(h, cudaEventRecord(h->ev2, h->stream));
+  k_cg_init<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->B, (const T*)h->d_dinv, (T*)h->X,
+                                            (T*)h->R, (T*)h->P, h->d_ctl, h->d_partials, rtol, atol,
+                                            imax);
+  h->stats.kernel_launches++;
+  CK(h, cudaGetLastError());
+  const int chunk = h->opts.check_every;
+  for (;;) {
+    CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PanelCtl), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->profile) harvest_profile(h);
+    if (h->h_ctl->nactive == 0) break;
+    int rc = run_chunk<T, KT>(h, chunk);
+    if (rc) return rc;
+  }
+  // true residual  AP = B - A X  (core.jl:640, 648-651)
+  launch_spmm<T, KT, 2>(h, (const T*)h->X, (T*)h->AP, (const T*)h->B);
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(h->ev3, h->stream));
+  CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PanelCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (h->profile) harvest_profile(h);
+  float ms = 0;
+  CK(h, cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+  h->stats.kernel_ms += ms;
+  return CS_B200_OK;
+}
+
+int gather_panel_status(cs_b200_handle* h, int kt, int64_t c0, int64_t* iters, double* relres,
+                        int64_t itmax, bool* any_fail, bool* any_maxit, std::string* msg) {
+  for (int c = 0; c < kt; ++c) {
+    const PanelCtl& ct = *h->h_ctl;
+    const double bn = ct.bnorm[c];
+    const double rr = bn > 0 ? std::sqrt(ct.resid[c] / bn) : 0.0;
+    if (iters) iters[c0 + c] = ct.iters[c];
+    if (relres) relres[c0 + c] = rr;
+    h->stats.iterations += ct.iters[c];
+    if (!(rr < h->opts.resid_gate)) {
+      if (!*any_fail) {
+        char buf[256];
+        snprintf(buf, sizeof buf,
+                 "CUDA PCG solver residual %g exceeds tolerance %g for column %lld (%d iterations)",
+                 rr, h->opts.resid_gate, (long long)(c0 + c + 1), ct.iters[c]);
+        *msg = buf;
+      }
+      *any_fail = true;
+    }
+    if (ct.iters[c] >= itmax && std::sqrt(ct.rho[c]) > ct.tol[c]) *any_maxit = true;
+  }
+  return 0;
+}
+
+int next_kt(int64_t remaining, int ktmax) {
+  int kt = ktmax;
+  while (kt > remaining) kt >>= 1;
+  return kt < 1 ? 1 : kt;
+}
+
+template <typename T, int KT>
+int pairs_panel(cs_b200_handle* h, int64_t c0, const int64_t* src, const int64_t* dst,
+                const double* weight, double rtol, int64_t itmax, T* R, T* volt, T* curr,
+                int accumulate, int64_t* iters, double* relres, bool* any_fail, bool* any_maxit,
+                std::string* msg) {
+  const size_t nelem = (size_t)h->n_pad * KT;
+  PanelCtl* hc = h->h_ctl;
+  std::memset(hc, 0, sizeof(PanelCtl));
+  for (int c = 0; c < KT; ++c) {
+    hc->src[c] = src[c0 + c];
+    hc->dst[c] = dst[c0 + c];
+    hc->weight[c] = weight ? weight[c0 + c] : 1.0;
+  }
+  CK(h, cudaMemcpyAsync(h->d_ctl, hc, sizeof(PanelCtl), cudaMemcpyHostToDevice, h->stream));
+  h->stats.h2d_bytes += sizeof(PanelCtl);
+  CK(h, cudaMemsetAsync(h->B, 0, nelem * sizeof(T), h->stream));
+  k_pair_rhs<T, KT><<<1, 32, 0, h->stream>>>((T*)h->B, h->d_ctl);
+  h->stats.kernel_launches++;
+  int rc = solve_panel<T, KT>(h, rtol, itmax);
+  if (rc) return rc;
+  k_pair_extract<T, KT><<<1, 32, 0, h->stream>>>((const T*)h->X, h->d_ctl);
+  h->stats.kernel_launches++;
+  if (accumulate || curr) {
+    const int grid = (int)std::min<int64_t>(h->grid_spmm, (h->n + (NT / KT) - 1) / (NT / KT));
+    k_cur_max<T, KT><<<grid, NT, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx,
+                                                 (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
+                                                 h->d_partials);
+    k_cur_acc<T, KT><<<grid, NT, 0, h->stream>>>(
+        (int)h->n, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
+        curr ? (T*)h->AP : nullptr, (T*)h->d_cum, (T*)h->d_max, accumulate,
+        h->opts.log_transform, KT);
+    h->stats.kernel_launches += 2;
+  }
+  CK(h, cudaGetLastError());
+  const int tg = (int)std::min<size_t>(4096, (nelem + 255) / 256);
+  if (curr) {
+    k_panel_to_cm<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->AP,
+                                                    (T*)h->stage, h->d_ctl, 0);
+    h->stats.kernel_launches++;
+    CK(h, cudaMemcpyAsync(curr + (size_t)c0 * h->n, h->stage, (size_t)h->n * KT * sizeof(T),
+                          cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (double)h->n * KT * sizeof(T);
+  }
+  if (volt) {
+    k_panel_to_cm<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->X,
+                                                    (T*)h->stage, h->d_ctl, 1);
+    h->stats.kernel_launches++;
+    CK(h, cudaMemcpyAsync(volt + (size_t)c0 * h->n, h->stage, (size_t)h->n * KT * sizeof(T),
+                          cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (double)h->n * KT * sizeof(T);
+  }
+  // status gathered from the host copy taken inside solve_panel; xsrc/xdst need a re-read
+  gather_panel_status(h, KT, c0, iters, relres, itmax, any_fail, any_maxit, msg);
+  CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PanelCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->stats.d2h_bytes += sizeof(PanelCtl);
+  for (int c = 0; c < KT; ++c) R[c0 + c] = (T)(h->h_ctl->xdst[c] - h->h_ctl->xsrc[c]);
+  return CS_B200_OK;
+}
+
+template <typename T, int KT>
+int rhs_panel(cs_b200_handle* h, int64_t c0, const T* rhs, T* lhs, double rtol, int64_t itmax,
+              int64_t* iters, double* relres, bool* any_fail, bool* any_maxit, std::string* msg) {
+  const size_t nelem = (size_t)h->n_pad * KT;
+  PanelCtl* hc = h->h_ctl;
+  std::memset(hc, 0, sizeof(PanelCtl));
+  for (int c = 0; c < KT; ++c) hc->src[c] = hc->dst[c] = -1;
+  CK(h, cudaMemcpyAsync(h->d_ctl, hc, sizeof(PanelCtl), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->stage, rhs + (size_t)c0 * h->n, (size_t)h->n * KT * sizeof(T),
+                        cudaMemcpyHostToDevice, h->stream));
+  h->stats.h2d_bytes += (double)h->n * KT * sizeof(T);
+  CK(h, cudaMemsetAsync(h->B, 0, nelem * sizeof(T), h->stream));
+  const int tg = (int)std::min<size_t>(4096, (nelem + 255) / 256);
+  k_cm_to_panel<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->stage,
+                                                  (T*)h->B, KT);
+  h->stats.kernel_launches++;
+  int rc = solve_panel<T, KT>(h, rtol, itmax);
+  if (rc) return rc;
+  gather_panel_status(h, KT, c0, iters, relres, itmax, any_fail, any_maxit, msg);
+  k_panel_to_cm<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->X,
+                                                  (T*)h->stage, h->d_ctl, 0);
+  h->stats.kernel_launches++;
+  CK(h, cudaMemcpyAsync(lhs + (size_t)c0 * h->n, h->stage, (size_t)h->n * KT * sizeof(T),
+                        cudaMemcpyDeviceToHost, h->stream));
+  h->stats.d2h_bytes += (double)h->n * KT * sizeof(T);
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CS_B200_OK;
+}
+
+#define DISPATCH_KT(kt, CALL)                    \
+  switch (kt) {                                  \
+    case 1: { constexpr int KT = 1; CALL; } break; \
+    case 2: { constexpr int KT = 2; CALL; } break; \
+    case 4: { constexpr int KT = 4; CALL; } break; \
+    default: { constexpr int KT = 8; CALL; } break; \
+  }
+
+template <typename T>
+int solve_pairs_t(cs_b200_handle* h, int64_t k, const int64_t* src, const int64_t* dst,
+                  const double* weight, double rtol, int64_t itmax, T* R, T* volt, T* curr,
+                  int accumulate, int64_t* iters, double* relres) {
+  bool any_fail = false, any_maxit = false;
+  std::string msg;
+  int64_t c0 = 0;
+  while (c0 < k) {
+    const int kt = next_kt(k - c0, h->ktmax);
+    int rc = 0;
+    DISPATCH_KT(kt, (rc = pairs_panel<T, KT>(h, c0, src, dst, weight, rtol, itmax, R, volt, curr,
+                                             accumulate, iters, relres, &any_fail, &any_maxit,
+                                             &msg)));
+    if (rc) return rc;
+    c0 += kt;
+  }
+  if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
+  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
+  return CS_B200_OK;
+}
+
+template <typename T>
+int solve_rhs_t(cs_b200_handle* h, int64_t k, const T* rhs, T* lhs, double rtol, int64_t itmax,
+                int64_t* iters, double* relres) {
+  bool any_fail = false, any_maxit = false;
+  std::string msg;
+  int64_t c0 = 0;
+  while (c0 < k) {
+    const int kt = next_kt(k - c0, h->ktmax);
+    int rc = 0;
+    DISPATCH_KT(kt, (rc = rhs_panel<T, KT>(h, c0, rhs, lhs, rtol, itmax, iters, relres, &any_fail,
+                                           &any_maxit, &msg)));
+    if (rc) return rc;
+    c0 += kt;
+  }
+  if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
+  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
+  return CS_B200_OK;
+}
+
+void begin_call(cs_b200_handle* h) {
+  cudaSetDevice(h->device);
+  h->err.clear();
+  const double setup = h->stats.setup_ms;
+  h->stats = cs_b200_stats{};
+  h->stats.setup_ms = setup;
+  cudaEventRecord(h->ev0, h->stream);
+}
+void end_call(cs_b200_handle* h) {
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.solve_ms = ms;
+}
+
+int ensure_flush(cs_b200_handle* h) {
+  if (h->d_flush) return 0;
+  h->flush_elems = (size_t)64 << 20;  // 256 MB of floats > 126 MB L2
+  CK(h, cudaMalloc(&h->d_flush, h->flush_elems * sizeof(float)));
+  CK(h, cudaMemsetAsync(h->d_flush, 0, h->flush_elems * sizeof(float), h->stream));
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int cs_b200_version(void) { return 1001; }
+
+const char* cs_b200_last_error(const cs_b200_handle* h) {
+  return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+int cs_b200_create(int64_t n, int64_t nnz, const void* rowptr, const void* colidx,
+                   const void* vals, int index_bits, int index_base, int dtype, int device,
+                   const cs_b200_opts* opts, cs_b200_handle** out) {
+  if (!out) return set_err(nullptr, CS_B200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (n <= 0 || nnz < 0 || !rowptr || (nnz > 0 && (!colidx || !vals)))
+    return set_err(nullptr, CS_B200_ERR_ARG, "bad matrix arguments (n=%lld nnz=%lld)",
+                   (long long)n, (long long)nnz);
+  if ((index_bits != 32 && index_bits != 64) || (index_base != 0 && index_base != 1) ||
+      (dtype != CS_B200_F32 && dtype != CS_B200_F64))
+    return set_err(nullptr, CS_B200_ERR_ARG, "bad index_bits/index_base/dtype");
+  if (nnz >= (int64_t)1 << 31 || n >= (int64_t)1 << 31)
+    return set_err(nullptr, CS_B200_ERR_UNSUPPORTED,
+                   "n and nnz must be < 2^31 (device indices are int32)");
+  cs_b200_handle* h = new cs_b200_handle();
+  h->n = n; h->nnz = nnz; h->dtype = dtype; h->device = device;
+  int rc = common_create(h, opts);
+  if (rc) { g_create_error = h->err; cs_b200_destroy(h); return rc; }
+  auto fail = [&](int code) { g_create_error = h->err; cs_b200_destroy(h); return code; };
+  cudaEventRecord(h->ev0, h->stream);
+  std::vector<int> rp, ci;
+  if (index_bits == 64) {
+    narrow_indices((const int64_t*)rowptr, n + 1, index_base, rp);
+    narrow_indices((const int64_t*)colidx, nnz, index_base, ci);
+  } else {
+    narrow_indices((const int32_t*)rowptr, n + 1, index_base, rp);
+    narrow_indices((const int32_t*)colidx, nnz, index_base, ci);
+  }
+  if (rp[0] != 0 || rp[n] != nnz) {
+    set_err(h, CS_B200_ERR_ARG, "rowptr does not span [0, nnz] (got %d..%d)", rp[0], rp[n]);
+    return fail(CS_B200_ERR_ARG);
+  }
+  const size_t es = h->esize();
+#define CKC(call)                                                                              \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (%s)", cudaGetErrorString(_e), #call);       \
+      return fail(CS_B200_ERR_CUDA);                                                           \
+    }                                                                                          \
+  } while (0)
+  CKC(cudaMalloc(&h->d_rowptr, (size_t)(n + 1) * sizeof(int)));
+  CKC(cudaMalloc(&h->d_colidx, std::max<size_t>(1, (size_t)nnz) * sizeof(int)));
+  CKC(cudaMalloc(&h->d_vals, std::max<size_t>(1, (size_t)nnz) * es));
+  CKC(cudaMemcpyAsync(h->d_rowptr, rp.data(), (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CKC(cudaMemcpyAsync(h->d_colidx, ci.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CKC(cudaMemcpyAsync(h->d_vals, vals, (size_t)nnz * es, cudaMemcpyHostToDevice, h->stream));
+  rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp) : finish_setup<float>(h, rp);
+  if (rc) return fail(rc);
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.setup_ms = ms;
+  *out = h;
+  return CS_B200_OK;
+}
+
+int cs_b200_create_from_device(int64_t n, int64_t nnz, const int32_t* d_rowptr,
+                               const int32_t* d_colidx, const void* d_vals, int dtype, int device,
+                               const cs_b200_opts* opts, cs_b200_handle** out) {
+  if (!out) return set_err(nullptr, CS_B200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (n <= 0 || nnz <= 0 || !d_rowptr || !d_colidx || !d_vals ||
+      (dtype != CS_B200_F32 && dtype != CS_B200_F64) || nnz >= (int64_t)1 << 31)
+    return set_err(nullptr, CS_B200_ERR_ARG, "bad arguments");
+  cs_b200_handle* h = new cs_b200_handle();
+  h->n = n; h->nnz = nnz; h->dtype = dtype; h->device = device;
+  h->owns_matrix = false;
+  int rc = common_create(h, opts);
+  if (rc) { g_create_error = h->err; cs_b200_destroy(h); return rc; }
+  cudaEventRecord(h->ev0, h->stream);
+  h->d_rowptr = const_cast<int*>(d_rowptr);
+  h->d_colidx = const_cast<int*>(d_colidx);
+  h->d_vals = const_cast<void*>(d_vals);
+  std::vector<int> rp(n + 1);
+  cudaError_t e = cudaMemcpy(rp.data(), d_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    set_err(h, CS_B200_ERR_CUDA, "CUDA error %s reading rowptr", cudaGetErrorString(e));
+    g_create_error = h->err; cs_b200_destroy(h); return CS_B200_ERR_CUDA;
+  }
+  rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp) : finish_setup<float>(h, rp);
+  if (rc) { g_create_error = h->err; cs_b200_destroy(h); return rc; }
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.setup_ms = ms;
+  *out = h;
+  return CS_B200_OK;
+}
+
+void cs_b200_destroy(cs_b200_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->owns_matrix) { cudaFree(h->d_rowptr); cudaFree(h->d_colidx); cudaFree(h->d_vals); }
+  void* bufs[] = {h->d_dinv, h->d_bstart, h->X, h->R, h->P, h->AP, h->B, h->stage,
+                  h->d_cum, h->d_max, h->d_ctl, h->d_partials, h->d_flush};
+  for (void* b : bufs) if (b) cudaFree(b);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev2) cudaEventDestroy(h->ev2);
+  if (h->ev3) cudaEventDestroy(h->ev3);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int cs_b200_reset_currents(cs_b200_handle* h) {
+  if (!h) return CS_B200_ERR_ARG;
+  cudaSetDevice(h->device);
+  CK(h, cudaMemsetAsync(h->d_cum, 0, (size_t)h->n_pad * h->esize(), h->stream));
+  const int g = (int)std::min<int64_t>(4096, (h->n_pad + 255) / 256);
+  if (h->dtype == CS_B200_F64)
+    k_fill<double><<<g, 256, 0, h->stream>>>((double*)h->d_max, (size_t)h->n_pad, -9999.0);
+  else
+    k_fill<float><<<g, 256, 0, h->stream>>>((float*)h->d_max, (size_t)h->n_pad, -9999.0f);
+  CK(h, cudaGetLastError());
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CS_B200_OK;
+}
+
+int cs_b200_read_currents(cs_b200_handle* h, void* cum, void* max) {
+  if (!h) return CS_B200_ERR_ARG;
+  cudaSetDevice(h->device);
+  if (cum) CK(h, cudaMemcpyAsync(cum, h->d_cum, (size_t)h->n * h->esize(), cudaMemcpyDeviceToHost, h->stream));
+  if (max) CK(h, cudaMemcpyAsync(max, h->d_max, (size_t)h->n * h->esize(), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CS_B200_OK;
+}
+
+int cs_b200_currents_device_ptrs(cs_b200_handle* h, void** d_cum, void** d_max) {
+  if (!h) return CS_B200_ERR_ARG;
+  if (d_cum) *d_cum = h->d_cum;
+  if (d_max) *d_max = h->d_max;
+  return CS_B200_OK;
+}
+
+int cs_b200_stream(cs_b200_handle* h, void** stream) {
+  if (!h || !stream) return CS_B200_ERR_ARG;
+  *stream = (void*)h->stream;
+  return CS_B200_OK;
+}
+
+int cs_b200_profile_spmm(cs_b200_handle* h, int enable, double* total_ms, int64_t* launches) {
+  if (!h) return CS_B200_ERR_ARG;
+  if (total_ms) *total_ms = h->prof_ms;
+  if (launches) *launches = h->prof_launches;
+  if (enable >= 0) {
+    h->profile = enable ? 1 : 0;
+    h->prof_ms = 0.0;
+    h->prof_launches = 0;
+    h->prof_used = 0;
+  }
+  return CS_B200_OK;
+}
+
+int cs_b200_get_stats(const cs_b200_handle* h, cs_b200_stats* out) {
+  if (!h || !out) return CS_B200_ERR_ARG;
+  *out = h->stats;
+  return CS_B200_OK;
+}
+
+int cs_b200_spmv(cs_b200_handle* h, const void* x, void* y, int reps, double* ms_per_rep) {
+  if (!h || !x || !y || reps < 1) return set_err(h, CS_B200_ERR_ARG, "bad spmv arguments");
+  begin_call(h);
+  const size_t bytes = (size_t)h->n * h->esize();
+  CK(h, cudaMemcpyAsync(h->X, x, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaEventRecord(h->ev2, h->stream));
+  for (int r = 0; r < reps; ++r) {
+    if (h->dtype == CS_B200_F64)
+      launch_spmm<double, 1, 0>(h, (const double*)h->X, (double*)h->AP, nullptr);
+    else
+      launch_spmm<float, 1, 0>(h, (const float*)h->X, (float*)h->AP, nullptr);
+  }
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(h->ev3, h->stream));
+  CK(h, cudaMemcpyAsync(y, h->AP, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(h, cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+  if (ms_per_rep) *ms_per_rep = ms / reps;
+  h->stats.kernel_ms = ms;
+  h->stats.h2d_bytes = h->stats.d2h_bytes = (double)bytes;
+  end_call(h);
+  return CS_B200_OK;
+}
+
+int cs_b200_bench_spmm(cs_b200_handle* h, int k, int reps, int flush_l2, double* ms_per_rep) {
+  if (!h || reps < 1 || (k != 1 && k != 2 && k != 4 && k != 8) || k > h->ktmax)
+    return set_err(h, CS_B200_ERR_ARG, "bad bench_spmm arguments");
+  begin_call(h);
+  if (flush_l2) { int rc = ensure_flush(h); if (rc) return rc; }
+  const size_t pe = (size_t)h->n_pad * k;
+  const int g = (int)std::min<size_t>(4096, (pe + 255) / 256);
+  if (h->dtype == CS_B200_F64) k_fill<double><<<g, 256, 0, h->stream>>>((double*)h->X, pe, 1.0);
+  else k_fill<float><<<g, 256, 0, h->stream>>>((float*)h->X, pe, 1.0f);
+  double total = 0;
+  auto one = [&]() {
+    if (h->dtype == CS_B200_F64) { DISPATCH_KT(k, (launch_spmm<double, KT, 0>(h, (const double*)h->X, (double*)h->AP, nullptr))); }
+    else { DISPATCH_KT(k, (launch_spmm<float, KT, 0>(h, (const float*)h->X, (float*)h->AP, nullptr))); }
+  };
+  one();  // warm-up
+  if (flush_l2) {
+    for (int r = 0; r < reps; ++r) {
+      k_flush<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_elems);
+      CK(h, cudaEventRecord(h->ev2, h->stream));
+      one();
+      CK(h, cudaEventRecord(h->ev3, h->stream));
+      CK(h, cudaEventSynchronize(h->ev3));
+      float ms = 0;
+      CK(h, cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+      total += ms;
+    }
+  } else {
+    CK(h, cudaEventRecord(h->ev2, h->stream));
+    for (int r = 0; r < reps; ++r) one();
+    CK(h, cudaEventRecord(h->ev3, h->stream));
+    CK(h, cudaEventSynchronize(h->ev3));
+    float ms = 0;
+    CK(h, cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+    total = ms;
+  }
+  CK(h, cudaGetLastError());
+  if (ms_per_rep) *ms_per_rep = total / reps;
+  h->stats.kernel_ms = total;
+  end_call(h);
+  return CS_B200_OK;
+}
+
+int cs_b200_bench_cg_iter(cs_b200_handle* h, int k, int reps, double* ms_per_rep) {
+  if (!h || reps < 1 || (k != 1 && k != 2 && k != 4 && k != 8) || k > h->ktmax)
+    return set_err(h, CS_B200_ERR_ARG, "bad bench_cg_iter arguments");
+  begin_call(h);
+  PanelCtl* hc = h->h_ctl;
+  std::memset(hc, 0, sizeof(PanelCtl));
+  for (int c = 0; c < k; ++c) {
+    hc->src[c] = (c * 7919) % h->n;
+    hc->dst[c] = h->n - 1 - (c * 104729) % (h->n / 2 + 1);
+    if (hc->dst[c] == hc->src[c]) hc->dst[c] = (hc->src[c] + 1) % h->n;
+    hc->weight[c] = 1.0;
+  }
+  CK(h, cudaMemcpyAsync(h->d_ctl, hc, sizeof(PanelCtl), cudaMemcpyHostToDevice, h->stream));
+  const size_t nelem = (size_t)h->n_pad * k;
+  CK(h, cudaMemsetAsync(h->B, 0, nelem * h->esize(), h->stream));
+  const bool f64 = h->dtype == CS_B200_F64;
+#define BOTH(CALLD, CALLF) do { if (f64) { DISPATCH_KT(k, CALLD); } else { DISPATCH_KT(k, CALLF); } } while (0)
+  BOTH((k_pair_rhs<double, KT><<<1, 32, 0, h->stream>>>((double*)h->B, h->d_ctl)),
+       (k_pair_rhs<float, KT><<<1, 32, 0, h->stream>>>((float*)h->B, h->d_ctl)));
+  BOTH((k_cg_init<double, KT><<<ew_grid<double, KT>(h), NT, 0, h->stream>>>(nelem, (const double*)h->B, (const double*)h->d_dinv, (double*)h->X, (double*)h->R, (double*)h->P, h->d_ctl, h->d_partials, 0.0, 0.0, 1 << 30)),
+       (k_cg_init<float, KT><<<ew_grid<float, KT>(h), NT, 0, h->stream>>>(nelem, (const float*)h->B, (const float*)h->d_dinv, (float*)h->X, (float*)h->R, (float*)h->P, h->d_ctl, h->d_partials, 0.0, 0.0, 1 << 30)));
+  for (int w = 0; w < 3; ++w) BOTH((launch_iteration<double, KT>(h)), (launch_iteration<float, KT>(h)));
+  CK(h, cudaEventRecord(h->ev2, h->stream));
+  for (int r = 0; r < reps; ++r) BOTH((launch_iteration<double, KT>(h)), (launch_iteration<float, KT>(h)));
+  CK(h, cudaEventRecord(h->ev3, h->stream));
+  CK(h, cudaEventSynchronize(h->ev3));
+  CK(h, cudaGetLastError());
+  float ms = 0;
+  CK(h, cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+  if (ms_per_rep) *ms_per_rep = ms / reps;
+  h->stats.kernel_ms = ms;
+  end_call(h);
+  return CS_B200_OK;
+}
+
+int cs_b200_solve_rhs(cs_b200_handle* h, int64_t k, const void* rhs, void* lhs, double rtol,
+                      int64_t itmax, int64_t* iters, double* relres) {
+  if (!h || k < 1 || !rhs || !lhs || !(rtol >= 0) || itmax < 0)
+    return set_err(h, CS_B200_ERR_ARG, "bad solve_rhs arguments");
+  begin_call(h);
+  int rc = h->dtype == CS_B200_F64
+               ? solve_rhs_t<double>(h, k, (const double*)rhs, (double*)lhs, rtol, itmax, iters, relres)
+               : solve_rhs_t<float>(h, k, (const float*)rhs, (float*)lhs, rtol, itmax, iters, relres);
+  end_call(h);
+  return rc;
+}
+
+int cs_b200_solve_pairs(cs_b200_handle* h, int64_t k, const int64_t* src, const int64_t* dst,
+                        const double* weight, double rtol, int64_t itmax, void* R, void* volt,
+                        void* curr, int accumulate, int64_t* iters, double* relres) {
+  if (!h || k < 1 || !src || !dst || !R || !(rtol >= 0) || itmax < 0)
+    return set_err(h, CS_B200_ERR_ARG, "bad solve_pairs arguments");
+  for (int64_t c = 0; c < k; ++c)
+    if (src[c] < 0 || src[c] >= h->n || dst[c] < 0 || dst[c] >= h->n || src[c] == dst[c])
+      return set_err(h, CS_B200_ERR_ARG, "pair %lld: src/dst out of range or equal (%lld, %lld)",
+                     (long long)c, (long long)src[c], (long long)dst[c]);
+  begin_call(h);
+  int rc = h->dtype == CS_B200_F64
+               ? solve_pairs_t<double>(h, k, src, dst, weight, rtol, itmax, (double*)R,
+                                       (double*)volt, (double*)curr, accumulate, iters, relres)
+               : solve_pairs_t<float>(h, k, src, dst, weight, rtol, itmax, (float*)R, (float*)volt,
+                                      (float*)curr, accumulate, iters, relres);
+  end_call(h);
+  return rc;
+}
+
+}  // extern "C"

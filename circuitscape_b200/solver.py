@@ -1,0 +1,221 @@
+"""Host-side mirror of the reference's Solver plug-in surface for the CUDA path.
+
+Same names, argument meaning and error behaviour as the methods a Circuitscape.jl
+package extension overloads (ext/CircuitscapePardisoExt.jl:31-45,
+ext/CircuitscapeAppleAccelerateExt.jl:8-22; generics in src/core.jl:519-523,
+646-653 and src/raster/advanced.jl:307-333):
+
+    construct_cholesky_factor(matrix, solver)       -> B200Factor   (hook #1)
+    solve_linear_system(factor, matrix, rhs)        -> lhs          (hook #2)
+    multiple_solve(solver, matrix, sources)         -> volt         (hook #3)
+
+`B200Factor` is the opaque "factor" object: it owns a `cs_b200_handle*`.  The Julia
+glue of INTEGRATION.md is a line-for-line twin of this file using `ccall`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+
+# solver-name table (reference: src/consts.jl:12-15 AMG/CHOLMOD/PARDISO/ACCELERATE)
+CUDAB200 = ["cuda", "gpu", "b200", "cg+jacobi+cuda", "cg+amg+cuda"]
+
+
+@dataclass
+class CUDASolver:
+    """`struct CUDASolver <: Solver; bs::Int end` -- bs = cfg.cholmod_batch_size
+    (src/core.jl:57-63, 81-90).  Extra knobs are this path's own."""
+    bs: int = 1000
+    precision: str = "double"        # cfg.precision  (src/run.jl:29)
+    device: int = 0
+    rtol: float = 1e-6               # src/core.jl:639
+    itmax: int = 100_000             # src/core.jl:639
+    precond: str = "jacobi"
+    panel_width: int = 8
+    check_every: int = 16
+    use_graph: bool = True
+
+    @property
+    def dtype(self):
+        return np.float32 if self.precision in ("single", "Single") else np.float64
+
+
+class SolverResidualError(RuntimeError):
+    """The reference's `error("... residual $r exceeds tolerance 1e-4 ...")`
+    (src/core.jl:641,650)."""
+
+
+class B200Factor:
+    """Opaque factor: CSR + preconditioner resident on one B200 (cs_b200_create)."""
+
+    def __init__(self, matrix, solver: CUDASolver, log_transform=False):
+        lib = _lib.load()
+        self._lib = lib
+        self._h = C.c_void_p()
+        m = sp.csr_matrix(matrix)
+        m.sort_indices()
+        self.n = m.shape[0]
+        self.dtype = np.dtype(solver.dtype)
+        self.solver = solver
+        vals = np.ascontiguousarray(m.data, dtype=self.dtype)
+        rowptr = np.ascontiguousarray(m.indptr)
+        colidx = np.ascontiguousarray(m.indices)
+        bits = 64 if rowptr.dtype == np.int64 else 32
+        if colidx.dtype != rowptr.dtype:
+            colidx = colidx.astype(rowptr.dtype)
+        opts = _lib.Opts()
+        opts.precond = _lib.PRECOND_AMG if solver.precond == "amg" else _lib.PRECOND_JACOBI
+        opts.panel_width = solver.panel_width
+        opts.check_every = solver.check_every
+        opts.use_graph = 1 if solver.use_graph else -1
+        opts.log_transform = 1 if log_transform else 0
+        rc = lib.cs_b200_create(self.n, m.nnz, _lib._ptr(rowptr), _lib._ptr(colidx), _lib._ptr(vals),
+                                bits, 0, _lib.dtype_code(self.dtype), solver.device,
+                                C.byref(opts), C.byref(self._h))
+        _lib.check(lib, None, rc)
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.cs_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- calls ------------------------------------------------------------
+    def stats(self):
+        st = _lib.Stats()
+        self._lib.cs_b200_get_stats(self._h, C.byref(st))
+        return st.as_dict()
+
+    def stream_ptr(self):
+        p = C.c_void_p()
+        _lib.check(self._lib, self._h, self._lib.cs_b200_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def profile_spmm(self, enable):
+        """enable True/False: start/stop per-launch SpMM timing; returns (ms, launches)
+        accumulated since the previous enable."""
+        ms, cnt = C.c_double(), C.c_int64()
+        _lib.check(self._lib, self._h,
+                   self._lib.cs_b200_profile_spmm(self._h, -1 if enable is None else int(bool(enable)),
+                                                  C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    def spmv(self, x, reps=1):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        y = np.empty_like(x)
+        ms = C.c_double()
+        rc = self._lib.cs_b200_spmv(self._h, _lib._ptr(x), _lib._ptr(y), reps, C.byref(ms))
+        _lib.check(self._lib, self._h, rc)
+        return y, ms.value
+
+    def bench_spmm(self, k, reps=20, flush_l2=False):
+        ms = C.c_double()
+        rc = self._lib.cs_b200_bench_spmm(self._h, k, reps, 1 if flush_l2 else 0, C.byref(ms))
+        _lib.check(self._lib, self._h, rc)
+        return ms.value
+
+    def bench_cg_iter(self, k, reps=20):
+        ms = C.c_double()
+        rc = self._lib.cs_b200_bench_cg_iter(self._h, k, reps, C.byref(ms))
+        _lib.check(self._lib, self._h, rc)
+        return ms.value
+
+    def solve_rhs(self, rhs, rtol=None, itmax=None, raise_on_residual=True):
+        """rhs: (n,) or (n, k).  Returns (lhs, iters, relres)."""
+        rhs = np.asarray(rhs, dtype=self.dtype)
+        vec = rhs.ndim == 1
+        b = np.asfortranarray(rhs.reshape(self.n, -1))
+        k = b.shape[1]
+        x = np.empty_like(b, order="F")
+        iters = np.zeros(k, dtype=np.int64)
+        relres = np.zeros(k, dtype=np.float64)
+        rc = self._lib.cs_b200_solve_rhs(self._h, k, _lib._ptr(b), _lib._ptr(x),
+                                         self.solver.rtol if rtol is None else rtol,
+                                         self.solver.itmax if itmax is None else itmax,
+                                         _lib._ptr(iters), _lib._ptr(relres))
+        self._raise(rc, raise_on_residual)
+        return (x[:, 0] if vec else x), iters, relres
+
+    def solve_pairs(self, src, dst, weight=None, want_volt=False, want_curr=False,
+                    accumulate=False, rtol=None, itmax=None, raise_on_residual=True):
+        """Batched focal-pair solve (src/dst 0-based rows).  Returns dict with
+        R (k,), volt (n,k)|None, curr (n,k)|None, iters, relres."""
+        src = np.ascontiguousarray(src, dtype=np.int64)
+        dst = np.ascontiguousarray(dst, dtype=np.int64)
+        k = len(src)
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        R = np.zeros(k, dtype=self.dtype)
+        volt = np.empty((self.n, k), dtype=self.dtype, order="F") if want_volt else None
+        curr = np.empty((self.n, k), dtype=self.dtype, order="F") if want_curr else None
+        iters = np.zeros(k, dtype=np.int64)
+        relres = np.zeros(k, dtype=np.float64)
+        rc = self._lib.cs_b200_solve_pairs(self._h, k, _lib._ptr(src), _lib._ptr(dst), _lib._ptr(w),
+                                           self.solver.rtol if rtol is None else rtol,
+                                           self.solver.itmax if itmax is None else itmax,
+                                           _lib._ptr(R), _lib._ptr(volt), _lib._ptr(curr),
+                                           1 if accumulate else 0, _lib._ptr(iters), _lib._ptr(relres))
+        self._raise(rc, raise_on_residual)
+        return dict(R=R, volt=volt, curr=curr, iters=iters, relres=relres)
+
+    def read_currents(self, want_max=True):
+        cum = np.empty(self.n, dtype=self.dtype)
+        mx = np.empty(self.n, dtype=self.dtype) if want_max else None
+        rc = self._lib.cs_b200_read_currents(self._h, _lib._ptr(cum), _lib._ptr(mx))
+        _lib.check(self._lib, self._h, rc)
+        return cum, mx
+
+    def reset_currents(self):
+        _lib.check(self._lib, self._h, self._lib.cs_b200_reset_currents(self._h))
+
+    def currents_device_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        _lib.check(self._lib, self._h, self._lib.cs_b200_currents_device_ptrs(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def _raise(self, rc, raise_on_residual):
+        if rc == _lib.OK:
+            return
+        if rc == _lib.ERR_RESIDUAL:
+            if raise_on_residual:
+                msg = self._lib.cs_b200_last_error(self._h).decode()
+                raise SolverResidualError(msg)
+            return
+        if rc == _lib.ERR_MAXITER:
+            return  # results written; the residual gate decides (reference: itmax then gate)
+        _lib.check(self._lib, self._h, rc)
+
+
+# ---------------------------------------------------------------------------
+# the three plug-in hooks
+# ---------------------------------------------------------------------------
+def construct_cholesky_factor(matrix, solver: CUDASolver, **kw) -> B200Factor:
+    """Hook #1 (src/core.jl:379,519-523): once per connected component."""
+    return B200Factor(matrix, solver, **kw)
+
+
+def solve_linear_system(factor: B200Factor, matrix, rhs):
+    """Hook #2 (src/core.jl:463,646-653): n x k -> n x k; raises if any column's
+    true relative residual is >= 1e-4, like every reference solver."""
+    lhs, _, _ = factor.solve_rhs(rhs)
+    return lhs
+
+
+def multiple_solve(solver: CUDASolver, matrix, sources):
+    """Hook #3 (src/raster/advanced.jl:307-333): factor + one solve + the
+    reference's `@assert residual < 1e-4`."""
+    with construct_cholesky_factor(matrix, solver) as factor:
+        volt = solve_linear_system(factor, matrix, np.asarray(sources))
+    return volt

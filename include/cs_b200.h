@@ -1,0 +1,162 @@
+/*
+ * cs_b200.h -- C ABI of libcsb200.so: a B200-native (sm_100a) replacement for the
+ * inner Laplacian-solve loop of Circuitscape.jl (pairwise + advanced mode).
+ *
+ * This is the drop-in boundary.  The reference (Julia) reaches a solver through
+ * three methods that package extensions overload (ext/CircuitscapePardisoExt.jl:31-45,
+ * ext/CircuitscapeAppleAccelerateExt.jl:8-22):
+ *
+ *   construct_cholesky_factor(matrix, solver)          src/core.jl:379,519-523
+ *        -> cs_b200_create            (once per connected component)
+ *   solve_linear_system(factor, matrix, rhs::Matrix)   src/core.jl:463,646-653
+ *        -> cs_b200_solve_rhs         (n x k column-major in, n x k out, true
+ *                                      residual gate 1e-4 reported per column)
+ *   multiple_solve(solver, matrix, sources::Vector)    src/raster/advanced.jl:307-333
+ *        -> cs_b200_create + cs_b200_solve_rhs(k = 1)
+ *
+ * and the batched driver around them (src/core.jl:312-515: RHS  -1 at src, +1 at
+ * dst; shift so v[src] = 0; R = v[dst] - v[src]; per-pair node currents
+ * src/out.jl:178-290 accumulated into cumulative / max maps src/out.jl:100-107)
+ * is offered as ONE device-resident call so n x k voltages never cross PCIe:
+ *
+ *        -> cs_b200_solve_pairs  + cs_b200_read_currents
+ *
+ * All entry points use plain pointers and sizes; every function returns 0 on
+ * success or a negative cs_b200_status; cs_b200_last_error() gives the text.
+ * Host buffers are copied during the call (the caller keeps ownership; Julia:
+ * GC.@preserve).  A handle is NOT re-entrant: one in-flight call per handle.
+ * INTEGRATION.md shows the Julia `ccall` glue that binds these symbols.
+ */
+#ifndef CS_B200_H
+#define CS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cs_b200_handle cs_b200_handle;
+
+enum cs_b200_status {
+  CS_B200_OK = 0,
+  CS_B200_ERR_ARG = -1,        /* bad argument                                    */
+  CS_B200_ERR_CUDA = -2,       /* CUDA runtime error (no GPU, OOM, launch failure) */
+  CS_B200_ERR_RESIDUAL = -3,   /* a column failed the true-residual gate (1e-4), the
+                                  reference's `error("... exceeds tolerance 1e-4")`,
+                                  src/core.jl:641,650                              */
+  CS_B200_ERR_MAXITER = -4,    /* itmax reached before rtol (results still written) */
+  CS_B200_ERR_UNSUPPORTED = -5
+};
+
+enum cs_b200_dtype { CS_B200_F32 = 0, CS_B200_F64 = 1 };
+
+enum cs_b200_precond {
+  CS_B200_PRECOND_JACOBI = 0,  /* D^-1, built on device                            */
+  CS_B200_PRECOND_AMG = 1      /* aggregation multigrid V-cycle, Jacobi-smoothed
+                                  (the reference's AMG role, src/core.jl:164-167)  */
+};
+
+/* Options; zero-initialise then override.  0 means "library default".             */
+typedef struct cs_b200_opts {
+  int32_t precond;        /* cs_b200_precond                                       */
+  int32_t panel_width;    /* RHS columns solved together per panel: 1,2,4,8 (def 8) */
+  int32_t check_every;    /* CG iterations between host convergence polls (def 16)  */
+  int32_t use_graph;      /* capture the iteration chunk in a CUDA graph (def 1)    */
+  double atol;            /* absolute term of the stop test; 0 => sqrt(eps(T)), the
+                             Krylov.jl default in force at src/core.jl:639; <0 => none */
+  double resid_gate;      /* true-residual gate (def 1e-4, src/core.jl:641)         */
+  int32_t log_transform;  /* current maps accumulate log10(c) (src/out.jl:305-309)  */
+  int32_t reserved[7];
+} cs_b200_opts;
+
+/* Per-call statistics (milliseconds measured with CUDA events on the solve stream). */
+typedef struct cs_b200_stats {
+  double setup_ms;        /* create: upload + preconditioner build                  */
+  double solve_ms;        /* last solve_*: device time incl. H2D/D2H inside the call */
+  double kernel_ms;       /* last solve_*: iteration kernels only                   */
+  int64_t iterations;     /* last solve_*: sum over columns                         */
+  int64_t spmm_launches;  /* last solve_*: SpMM kernel launches                     */
+  int64_t kernel_launches;/* last solve_*: all kernel launches                      */
+  double h2d_bytes, d2h_bytes;
+} cs_b200_stats;
+
+/* Build the device-resident operator for one connected component.
+ * CSR of a symmetric matrix (so Julia's SparseMatrixCSC colptr/rowval/nzval can be
+ * passed as-is).  index_bits in {32,64}: width of rowptr/colidx entries;
+ * index_base in {0,1}; dtype: type of `vals`, of all RHS/solution buffers and of the
+ * device arithmetic.  device: CUDA ordinal.  opts may be NULL.                      */
+int cs_b200_create(int64_t n, int64_t nnz, const void* rowptr, const void* colidx,
+                   const void* vals, int index_bits, int index_base, int dtype,
+                   int device, const cs_b200_opts* opts, cs_b200_handle** out);
+
+/* Same, but rowptr/colidx/vals already live on `device` (int32 0-based indices,
+ * values of `dtype`).  Used after an NCCL broadcast of the matrix to peer GPUs.    */
+int cs_b200_create_from_device(int64_t n, int64_t nnz, const int32_t* d_rowptr,
+                               const int32_t* d_colidx, const void* d_vals, int dtype,
+                               int device, const cs_b200_opts* opts, cs_b200_handle** out);
+
+void cs_b200_destroy(cs_b200_handle* h);
+
+/* Text of the last error on this handle (or of the last failed create if h==NULL). */
+const char* cs_b200_last_error(const cs_b200_handle* h);
+
+/* y = A x, `reps` times back to back; *ms_per_rep = mean device time of one SpMV
+ * (CUDA events).  x, y: host vectors of n values of the handle's dtype.  Benchmark
+ * and parity hook for the headline kernel.                                          */
+int cs_b200_spmv(cs_b200_handle* h, const void* x, void* y, int reps, double* ms_per_rep);
+
+/* Y = A X for a row-major n x k panel resident on the device (k in 1,2,4,8),
+ * timing only -- no host traffic.  flush_l2 != 0 writes a >L2 buffer between reps. */
+int cs_b200_bench_spmm(cs_b200_handle* h, int k, int reps, int flush_l2, double* ms_per_rep);
+
+/* One fused PCG iteration (SpMM+dot, residual update+dot, direction update) on a
+ * device-resident panel of width k, `reps` times; timing only.                      */
+int cs_b200_bench_cg_iter(cs_b200_handle* h, int k, int reps, double* ms_per_rep);
+
+/* solve_linear_system(factor, matrix, rhs): A X = B for k right-hand sides.
+ * rhs, lhs: host, column-major n x k (Julia Matrix / Vector when k = 1).
+ * iters[k], relres[k] (true relative residual ||A x - b|| / ||b||) may be NULL.
+ * Returns CS_B200_ERR_RESIDUAL if any column fails the gate (lhs still written).    */
+int cs_b200_solve_rhs(cs_b200_handle* h, int64_t k, const void* rhs, void* lhs,
+                      double rtol, int64_t itmax, int64_t* iters, double* relres);
+
+/* Batched focal-pair solve, device-resident:
+ *   for c in 0..k-1:  A v = e_dst[c] - e_src[c];  v -= v[src[c]];  R[c] = v[dst[c]]
+ * src/dst: 0-based rows of this component.  R: k values of dtype.
+ * volt: NULL or host column-major n x k (shifted voltages).
+ * If accumulate != 0 the node-current vector of every pair (src/out.jl:178-207:
+ * max(inflow, outflow) per node with the 1e-8 relative zeroing of src/out.jl:281-287)
+ * is added weight[c] times into the handle's cumulative vector and max-ed into its
+ * max vector (src/out.jl:100-107); weight == NULL means 1 each.
+ * curr: NULL or host column-major n x k of the per-pair node currents.              */
+int cs_b200_solve_pairs(cs_b200_handle* h, int64_t k, const int64_t* src, const int64_t* dst,
+                        const double* weight, double rtol, int64_t itmax, void* R,
+                        void* volt, void* curr, int accumulate, int64_t* iters,
+                        double* relres);
+
+/* Cumulative / max node-current vectors (n values of dtype each; either may be
+ * NULL).  max is initialised to -9999 like src/utils.jl:124.                        */
+int cs_b200_read_currents(cs_b200_handle* h, void* cum, void* max);
+int cs_b200_reset_currents(cs_b200_handle* h);
+/* Device pointers of the same vectors (for an NCCL reduce across ranks).            */
+int cs_b200_currents_device_ptrs(cs_b200_handle* h, void** d_cum, void** d_max);
+
+int cs_b200_get_stats(const cs_b200_handle* h, cs_b200_stats* out);
+
+/* The CUDA stream (cudaStream_t) every kernel of this handle is launched on, so a
+ * caller can bracket calls with its own CUDA events.                                */
+int cs_b200_stream(cs_b200_handle* h, void** stream);
+
+/* Per-launch timing of the dominant kernel.  enable = 1/0 switches event pairs around
+ * every SpMM launch on/off (the CUDA-graph path is bypassed while on) and clears the
+ * totals; enable < 0 only reads.  *total_ms / *launches: totals since last enable.  */
+int cs_b200_profile_spmm(cs_b200_handle* h, int enable, double* total_ms, int64_t* launches);
+
+/* Library/ABI version: major*1000 + minor.                                          */
+int cs_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CS_B200_H */

@@ -126,3 +126,24 @@ def test_network_advanced(golden, i):
     v[:, :2] += 1
     assert mine.shape == v.shape
     assert np.sum((_sorted_rows(mine) - _sorted_rows(v)) ** 2) < TOL
+
+
+@pytest.mark.parametrize("i", [1, 2, 4, 9, 12, 14, 16, 17])
+def test_cg_amg_raster_pairwise(golden, i):
+    """the oracle's reference-behaviour mode (SA-AMG-preconditioned CG, rtol 1e-6,
+    src/core.jl:161-167,639) reproduces the goldens within the reference's bars."""
+    cfg, inp, exp = co.load_case(golden, f"sgVerify{i}")
+    r = co.raster_pairwise(cfg, inp, "cg+amg")
+    x = exp["resistances.out"]
+    assert np.all(np.abs(x - r.resistances) <= np.sqrt(TOL))
+    for (a, b), m in r.curmaps.items():
+        assert np.sum((m - exp[f"curmap_{a}_{b}.asc"]) ** 2) < TOL
+    if "cum_curmap.asc" in exp:
+        assert np.sum((r.cum_curmap - exp["cum_curmap.asc"]) ** 2) < TOL
+
+
+def test_cg_amg_advanced(golden):
+    cfg, inp, exp = co.load_case(golden, "mgVerify1")
+    r = co.raster_advanced(cfg, inp, "cg+amg")
+    assert np.sum((r.curmap - exp["curmap.asc"]) ** 2) < TOL
+    assert np.sum((r.voltmap - exp["voltmap.asc"]) ** 2) < TOL
