@@ -1,0 +1,284 @@
+// amg_host.hpp -- host-side setup of the smoothed-aggregation hierarchy used as the
+// CG preconditioner on the device (role of `smoothed_aggregation(matrix; ...)` at
+// src/core.jl:164-167 and src/raster/advanced.jl:308 of the reference).
+//
+// The hierarchy is built ONCE per connected component on the host from the CSR the
+// caller hands to cs_b200_create, then uploaded; every V-cycle runs on the GPU
+// (DESIGN.md §5).  Algorithm (Vanek/Mandel/Brezina smoothed aggregation):
+//   strength      every off-diagonal nonzero (symmetric strength, theta = 0)
+//   aggregation   greedy root + neighbourhood, leftovers join a neighbour
+//   tentative T   piecewise constant, columns normalised (candidate = ones)
+//   prolongator   P = (I - (4/3)/rho * D^-1 A) T,  rho = ||D^-1 A||_inf >= rho(D^-1 A)
+//   coarse op     A_c = P^T A P  (Galerkin)
+//   coarsest      dense symmetric pseudo-inverse (cyclic Jacobi eigen-solver)
+// The smoother on the device is damped Jacobi with omega = (4/3)/rho_l per level, so
+// the V(1,1) cycle is a symmetric positive (semi-)definite operator as CG requires.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+namespace csb_amg {
+
+struct Csr {
+  int64_t nrows = 0, ncols = 0;
+  std::vector<int> ptr, idx;
+  std::vector<double> val;
+  int64_t nnz() const { return (int64_t)idx.size(); }
+};
+
+struct HostLevel {
+  Csr A;                       // operator of this level
+  Csr P;                       // prolongator to this level from the next (nrows = n_l, ncols = n_{l+1})
+  Csr R;                       // P^T
+  std::vector<double> dinv;    // 1/diag(A)
+  double omega = 2.0 / 3.0;    // Jacobi damping of this level
+};
+
+struct Hierarchy {
+  std::vector<HostLevel> levels;     // levels.back() has no P/R
+  std::vector<double> coarse_pinv;   // dense n_c x n_c (row-major) pseudo-inverse of levels.back().A
+  double operator_complexity() const {
+    double s = 0;
+    for (auto& l : levels) s += (double)l.A.nnz();
+    return s / (double)levels[0].A.nnz();
+  }
+};
+
+inline Csr transpose(const Csr& a) {
+  Csr t;
+  t.nrows = a.ncols; t.ncols = a.nrows;
+  t.ptr.assign(t.nrows + 1, 0);
+  for (int c : a.idx) t.ptr[c + 1]++;
+  for (int64_t i = 0; i < t.nrows; ++i) t.ptr[i + 1] += t.ptr[i];
+  t.idx.resize(a.idx.size());
+  t.val.resize(a.val.size());
+  std::vector<int> cur(t.ptr.begin(), t.ptr.end() - 1);
+  for (int64_t r = 0; r < a.nrows; ++r)
+    for (int j = a.ptr[r]; j < a.ptr[r + 1]; ++j) {
+      const int d = cur[a.idx[j]]++;
+      t.idx[d] = (int)r;
+      t.val[d] = a.val[j];
+    }
+  return t;
+}
+
+// C = A * B (Gustavson, dense marker per output row; columns sorted on output)
+inline Csr spgemm(const Csr& a, const Csr& b) {
+  Csr c;
+  c.nrows = a.nrows; c.ncols = b.ncols;
+  c.ptr.assign(c.nrows + 1, 0);
+  std::vector<int> marker(b.ncols, -1);
+  std::vector<double> acc(b.ncols, 0.0);
+  std::vector<int> cols;
+  c.idx.reserve(a.idx.size());
+  c.val.reserve(a.idx.size());
+  for (int64_t i = 0; i < a.nrows; ++i) {
+    cols.clear();
+    for (int ja = a.ptr[i]; ja < a.ptr[i + 1]; ++ja) {
+      const int k = a.idx[ja];
+      const double av = a.val[ja];
+      for (int jb = b.ptr[k]; jb < b.ptr[k + 1]; ++jb) {
+        const int col = b.idx[jb];
+        if (marker[col] != (int)i) { marker[col] = (int)i; acc[col] = 0.0; cols.push_back(col); }
+        acc[col] += av * b.val[jb];
+      }
+    }
+    std::sort(cols.begin(), cols.end());
+    for (int col : cols) { c.idx.push_back(col); c.val.push_back(acc[col]); }
+    c.ptr[i + 1] = (int)c.idx.size();
+  }
+  return c;
+}
+
+// Greedy aggregation over the off-diagonal pattern.  agg[i] in [0, nagg) or -1 (isolated).
+inline int aggregate(const Csr& a, std::vector<int>& agg) {
+  const int64_t n = a.nrows;
+  agg.assign(n, -1);
+  std::vector<char> isolated(n, 0);
+  int nagg = 0;
+  // phase 1: a node whose whole neighbourhood is still free seeds an aggregate
+  for (int64_t i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    bool any = false, all_free = true;
+    for (int j = a.ptr[i]; j < a.ptr[i + 1] && all_free; ++j) {
+      const int c = a.idx[j];
+      if (c == i || a.val[j] == 0.0) continue;
+      any = true;
+      if (agg[c] >= 0) all_free = false;
+    }
+    if (!any) { isolated[i] = 1; continue; }
+    if (!all_free) continue;
+    agg[i] = nagg;
+    for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j)
+      if (a.idx[j] != i && a.val[j] != 0.0) agg[a.idx[j]] = nagg;
+    ++nagg;
+  }
+  // phase 2: leftovers join the aggregate of their strongest already-aggregated neighbour
+  const std::vector<int> seeded(agg);
+  for (int64_t i = 0; i < n; ++i) {
+    if (agg[i] >= 0 || isolated[i]) continue;
+    double best = 0.0;
+    int pick = -1;
+    for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j) {
+      const int c = a.idx[j];
+      if (c == i || seeded[c] < 0) continue;
+      const double w = std::fabs(a.val[j]);
+      if (w > best) { best = w; pick = seeded[c]; }
+    }
+    if (pick >= 0) agg[i] = pick;
+  }
+  // phase 3: whatever is left groups with its free neighbours
+  for (int64_t i = 0; i < n; ++i) {
+    if (agg[i] >= 0 || isolated[i]) continue;
+    agg[i] = nagg;
+    for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j) {
+      const int c = a.idx[j];
+      if (c != i && agg[c] < 0 && !isolated[c] && a.val[j] != 0.0) agg[c] = nagg;
+    }
+    ++nagg;
+  }
+  return nagg;
+}
+
+// dense symmetric pseudo-inverse by cyclic Jacobi rotations (n <= a few hundred)
+inline std::vector<double> dense_pinv(const Csr& a) {
+  const int n = (int)a.nrows;
+  std::vector<double> m((size_t)n * n, 0.0), v((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) {
+    v[(size_t)i * n + i] = 1.0;
+    for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j) m[(size_t)i * n + a.idx[j]] += a.val[j];
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) {
+      const double s = 0.5 * (m[(size_t)i * n + j] + m[(size_t)j * n + i]);
+      m[(size_t)i * n + j] = m[(size_t)j * n + i] = s;
+    }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) {
+      diag += m[(size_t)i * n + i] * m[(size_t)i * n + i];
+      for (int j = i + 1; j < n; ++j) off += m[(size_t)i * n + j] * m[(size_t)i * n + j];
+    }
+    if (off <= 1e-30 * (diag + 1e-300)) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = m[(size_t)p * n + q];
+        if (apq == 0.0) continue;
+        const double app = m[(size_t)p * n + p], aqq = m[(size_t)q * n + q];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double mkp = m[(size_t)k * n + p], mkq = m[(size_t)k * n + q];
+          m[(size_t)k * n + p] = c * mkp - s * mkq;
+          m[(size_t)k * n + q] = s * mkp + c * mkq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double mpk = m[(size_t)p * n + k], mqk = m[(size_t)q * n + k];
+          m[(size_t)p * n + k] = c * mpk - s * mqk;
+          m[(size_t)q * n + k] = s * mpk + c * mqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
+          v[(size_t)k * n + p] = c * vkp - s * vkq;
+          v[(size_t)k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  double lmax = 0.0;
+  for (int i = 0; i < n; ++i) lmax = std::max(lmax, std::fabs(m[(size_t)i * n + i]));
+  const double cut = lmax * 1e-10 * std::max(1, n);
+  std::vector<double> out((size_t)n * n, 0.0);
+  for (int e = 0; e < n; ++e) {
+    const double lam = m[(size_t)e * n + e];
+    if (std::fabs(lam) <= cut) continue;
+    const double inv = 1.0 / lam;
+    for (int i = 0; i < n; ++i) {
+      const double vi = v[(size_t)i * n + e] * inv;
+      if (vi == 0.0) continue;
+      for (int j = 0; j < n; ++j) out[(size_t)i * n + j] += vi * v[(size_t)j * n + e];
+    }
+  }
+  return out;
+}
+
+inline void diag_and_rho(const Csr& a, std::vector<double>& dinv, double& rho) {
+  const int64_t n = a.nrows;
+  dinv.assign(n, 0.0);
+  rho = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    double d = 0.0, s = 0.0;
+    for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j) {
+      if (a.idx[j] == i) d += a.val[j];
+      s += std::fabs(a.val[j]);
+    }
+    if (d != 0.0) {
+      dinv[i] = 1.0 / d;
+      rho = std::max(rho, s / std::fabs(d));
+    }
+  }
+  if (!(rho > 0.0)) rho = 1.0;
+}
+
+inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 96) {
+  Hierarchy h;
+  h.levels.emplace_back();
+  h.levels.back().A = std::move(a0);
+  for (;;) {
+    HostLevel& lv = h.levels.back();
+    double rho;
+    diag_and_rho(lv.A, lv.dinv, rho);
+    lv.omega = (4.0 / 3.0) / rho;
+    const int64_t n = lv.A.nrows;
+    if ((int)h.levels.size() >= max_levels || n <= max_coarse) break;
+    std::vector<int> agg;
+    const int nagg = aggregate(lv.A, agg);
+    if (nagg <= 0 || nagg >= n) break;
+    std::vector<double> cnt(nagg, 0.0);
+    for (int64_t i = 0; i < n; ++i) if (agg[i] >= 0) cnt[agg[i]] += 1.0;
+    // S = I - omega D^-1 A   applied to T on the fly:  P = T - omega D^-1 (A T)
+    Csr T;
+    T.nrows = n; T.ncols = nagg;
+    T.ptr.assign(n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+      if (agg[i] >= 0) { T.idx.push_back(agg[i]); T.val.push_back(1.0 / std::sqrt(cnt[agg[i]])); }
+      T.ptr[i + 1] = (int)T.idx.size();
+    }
+    Csr AT = spgemm(lv.A, T);
+    Csr P;
+    P.nrows = n; P.ncols = nagg;
+    P.ptr.assign(n + 1, 0);
+    P.idx.reserve(AT.idx.size());
+    P.val.reserve(AT.idx.size());
+    for (int64_t i = 0; i < n; ++i) {
+      const double sc = lv.omega * lv.dinv[i];
+      const int mine = agg[i];
+      const double tv = mine >= 0 ? 1.0 / std::sqrt(cnt[mine]) : 0.0;
+      bool placed = mine < 0;
+      for (int j = AT.ptr[i]; j < AT.ptr[i + 1]; ++j) {
+        const int c = AT.idx[j];
+        double v = -sc * AT.val[j];
+        if (!placed && c > mine) { P.idx.push_back(mine); P.val.push_back(tv); placed = true; }
+        if (c == mine) { v += tv; placed = true; }
+        P.idx.push_back(c);
+        P.val.push_back(v);
+      }
+      if (!placed) { P.idx.push_back(mine); P.val.push_back(tv); }
+      P.ptr[i + 1] = (int)P.idx.size();
+    }
+    Csr R = transpose(P);
+    Csr AP = spgemm(lv.A, P);
+    Csr Ac = spgemm(R, AP);
+    lv.P = std::move(P);
+    lv.R = std::move(R);
+    h.levels.emplace_back();
+    h.levels.back().A = std::move(Ac);
+  }
+  h.coarse_pinv = dense_pinv(h.levels.back().A);
+  return h;
+}
+
+}  // namespace csb_amg
