@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "amg_host.hpp"
 #include "kernels.cuh"
 
 using namespace csb;
@@ -25,9 +26,31 @@ thread_local std::string g_create_error;
 struct GraphSlot {
   cudaGraphExec_t exec = nullptr;
   int chunk = 0;
+  int64_t kernels = 0, spmms = 0;   // launches inside one graph replay
 };
 
 }  // namespace
+
+// one CSR resident on the device, with its row-block partition (type-erased values)
+struct DevCsr {
+  int* rowptr = nullptr;
+  int* colidx = nullptr;
+  void* vals = nullptr;
+  int* bstart = nullptr;
+  int nblocks = 0;
+  int nrows = 0;
+  int64_t nnz = 0;
+  int lpr = 1;  // lanes per row used by k_spmm for this matrix
+};
+
+// one multigrid level below the finest (the finest level aliases the handle's own CSR)
+struct DevLevel {
+  int64_t n = 0, n_pad = 0;
+  DevCsr A, P, R;          // P: this level <- next coarser ; R = P^T
+  void* dinv = nullptr;
+  double omega = 2.0 / 3.0;
+  void *x = nullptr, *b = nullptr, *t = nullptr, *y = nullptr;   // panels n_pad x ktmax
+};
 
 struct cs_b200_handle {
   int device = 0;
@@ -42,6 +65,12 @@ struct cs_b200_handle {
   int nblocks = 0;
   int ktmax = 8;
   void *X = nullptr, *R = nullptr, *P = nullptr, *AP = nullptr, *B = nullptr, *stage = nullptr;
+  void* Z = nullptr;                 // AMG: z = M^-1 r
+  DevCsr A0;                         // view of the finest operator (aliases d_rowptr/...)
+  std::vector<DevLevel> lv;          // lv[0] = finest (A aliases A0), lv.back() = coarsest
+  double* d_pinv = nullptr;          // dense pseudo-inverse of the coarsest operator
+  double amg_opc = 0.0;              // operator complexity
+  bool amg = false;
   void *d_cum = nullptr, *d_max = nullptr;
   PanelCtl* d_ctl = nullptr;
   PanelCtl* h_ctl = nullptr;  // pinned
@@ -102,14 +131,95 @@ void build_row_blocks(const std::vector<int>& rowptr, int64_t n, std::vector<int
   }
 }
 
+// upload one host CSR (double values) as a device CSR of T with its row blocks
 template <typename T>
-int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr) {
+int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d) {
+  d.nrows = (int)m.nrows;
+  d.nnz = m.nnz();
+  std::vector<int> bstart;
+  build_row_blocks(m.ptr, m.nrows, bstart);
+  d.nblocks = (int)bstart.size() - 1;
+  d.lpr = (m.nrows > 0 && (double)d.nnz / (double)m.nrows >= 20.0) ? 4 : 1;
+  std::vector<T> v(m.val.begin(), m.val.end());
+  CK(h, cudaMalloc(&d.rowptr, (size_t)(m.nrows + 1) * sizeof(int)));
+  CK(h, cudaMalloc(&d.colidx, std::max<size_t>(1, (size_t)d.nnz) * sizeof(int)));
+  CK(h, cudaMalloc(&d.vals, std::max<size_t>(1, (size_t)d.nnz) * sizeof(T)));
+  CK(h, cudaMalloc(&d.bstart, bstart.size() * sizeof(int)));
+  CK(h, cudaMemcpy(d.rowptr, m.ptr.data(), (size_t)(m.nrows + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(d.colidx, m.idx.data(), (size_t)d.nnz * sizeof(int), cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(d.vals, v.data(), (size_t)d.nnz * sizeof(T), cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(d.bstart, bstart.data(), bstart.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return CS_B200_OK;
+}
+
+void free_csr(DevCsr& d) {
+  cudaFree(d.rowptr); cudaFree(d.colidx); cudaFree(d.vals); cudaFree(d.bstart);
+  d = DevCsr{};
+}
+
+// Smoothed-aggregation hierarchy: built on the host (amg_host.hpp), resident on the device.
+template <typename T>
+int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<int>& ci,
+              const T* vals_host) {
+  csb_amg::Csr a0;
+  a0.nrows = a0.ncols = h->n;
+  a0.ptr = rp;
+  a0.idx = ci;
+  a0.val.assign(vals_host, vals_host + h->nnz);
+  csb_amg::Hierarchy hier = csb_amg::build_hierarchy(std::move(a0));
+  h->amg_opc = hier.operator_complexity();
+  const int nl = (int)hier.levels.size();
+  h->lv.resize(nl);
+  for (int l = 0; l < nl; ++l) {
+    const csb_amg::HostLevel& hl = hier.levels[l];
+    DevLevel& L = h->lv[l];
+    L.n = hl.A.nrows;
+    L.n_pad = (L.n + 3) / 4 * 4;
+    L.omega = hl.omega;
+    if (l == 0) {
+      L.A = h->A0;  // alias, not owned
+      L.dinv = h->d_dinv;
+    } else {
+      int rc = upload_csr<T>(h, hl.A, L.A);
+      if (rc) return rc;
+      std::vector<T> dv(L.n_pad, T(0));
+      for (int64_t i = 0; i < L.n; ++i) dv[i] = (T)hl.dinv[i];
+      CK(h, cudaMalloc(&L.dinv, (size_t)L.n_pad * sizeof(T)));
+      CK(h, cudaMemcpy(L.dinv, dv.data(), (size_t)L.n_pad * sizeof(T), cudaMemcpyHostToDevice));
+      const size_t pe = (size_t)L.n_pad * h->ktmax * sizeof(T);
+      void** bufs[] = {&L.x, &L.b, &L.t, &L.y};
+      for (void** bp : bufs) {
+        CK(h, cudaMalloc(bp, pe));
+        CK(h, cudaMemset(*bp, 0, pe));
+      }
+    }
+    if (l + 1 < nl) {
+      int rc = upload_csr<T>(h, hl.P, L.P);
+      if (rc) return rc;
+      rc = upload_csr<T>(h, hl.R, L.R);
+      if (rc) return rc;
+    }
+  }
+  const size_t nc = (size_t)hier.levels.back().A.nrows;
+  CK(h, cudaMalloc(&h->d_pinv, std::max<size_t>(1, nc * nc) * sizeof(double)));
+  CK(h, cudaMemcpy(h->d_pinv, hier.coarse_pinv.data(), nc * nc * sizeof(double), cudaMemcpyHostToDevice));
+  const size_t pe = (size_t)h->n_pad * h->ktmax * sizeof(T);
+  CK(h, cudaMalloc(&h->Z, pe));
+  CK(h, cudaMemset(h->Z, 0, pe));
+  h->amg = nl > 1;
+  return CS_B200_OK;
+}
+
+template <typename T>
+int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std::vector<int>* h_colidx,
+                 const T* h_vals) {
   std::vector<int> bstart;
   build_row_blocks(h_rowptr, h->n, bstart);
   h->nblocks = (int)bstart.size() - 1;
   CK(h, cudaMalloc(&h->d_bstart, bstart.size() * sizeof(int)));
   CK(h, cudaMemcpyAsync(h->d_bstart, bstart.data(), bstart.size() * sizeof(int),
                         cudaMemcpyHostToDevice, h->stream));
+  h->A0 = DevCsr{h->d_rowptr, h->d_colidx, h->d_vals, h->d_bstart, h->nblocks, (int)h->n, h->nnz, 1};
   const size_t pe = (size_t)h->n_pad * h->ktmax;
   void** bufs[] = {&h->X, &h->R, &h->P, &h->AP, &h->B, &h->stage};
   for (void** b : bufs) {
@@ -128,6 +238,20 @@ int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr) {
       (int)h->n, (int)h->n_pad, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (T*)h->d_dinv);
   CK(h, cudaGetLastError());
   CK(h, cudaStreamSynchronize(h->stream));
+  if (h->opts.precond == CS_B200_PRECOND_AMG) {
+    std::vector<int> ci_local;
+    std::vector<T> v_local;
+    if (!h_colidx) {  // matrix arrived on the device (NCCL broadcast): fetch a host copy for setup
+      ci_local.resize(h->nnz);
+      v_local.resize(h->nnz);
+      CK(h, cudaMemcpy(ci_local.data(), h->d_colidx, (size_t)h->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+      CK(h, cudaMemcpy(v_local.data(), h->d_vals, (size_t)h->nnz * sizeof(T), cudaMemcpyDeviceToHost));
+      h_colidx = &ci_local;
+      h_vals = v_local.data();
+    }
+    int rc = setup_amg<T>(h, h_rowptr, *h_colidx, h_vals);
+    if (rc) return rc;
+  }
   return cs_b200_reset_currents(h);
 }
 
@@ -141,9 +265,8 @@ int common_create(cs_b200_handle* h, const cs_b200_opts* opts) {
   if (pw != 1 && pw != 2 && pw != 4 && pw != 8)
     return set_err(h, CS_B200_ERR_ARG, "panel_width must be 1, 2, 4 or 8 (got %d)", pw);
   h->ktmax = pw;
-  if (h->opts.precond != CS_B200_PRECOND_JACOBI)
-    return set_err(h, CS_B200_ERR_UNSUPPORTED, "preconditioner %d not available in this build",
-                   h->opts.precond);
+  if (h->opts.precond != CS_B200_PRECOND_JACOBI && h->opts.precond != CS_B200_PRECOND_AMG)
+    return set_err(h, CS_B200_ERR_UNSUPPORTED, "unknown preconditioner %d", h->opts.precond);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -176,11 +299,20 @@ void narrow_indices(const I* src, int64_t count, int base, std::vector<int>& dst
 // ---------------------------------------------------------------------------
 // launch helpers (all on h->stream)
 // ---------------------------------------------------------------------------
+template <typename T>
+CsrDev<T> view(const DevCsr& m) {
+  return CsrDev<T>{m.rowptr, m.colidx, (const T*)m.vals, m.bstart, m.nblocks, m.nrows};
+}
+
+// Y = op(M X) with the fused epilogue MODE (kernels.cuh).  `timed`: counts as a launch of
+// the dominant kernel for the per-launch profile (finest-level operator only).
 template <typename T, int KT, int MODE>
-void launch_spmm(cs_b200_handle* h, const T* X, T* Y, const T* B) {
-  const int grid = std::min(h->grid_spmm, h->nblocks);
+void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const T* B, const T* dinv,
+                    double omega, bool timed) {
+  const int grid = std::max(1, std::min(h->grid_spmm, m.nblocks));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->profile) {
+  const bool prof = h->profile && timed;
+  if (prof) {
     if (h->prof_used + 2 > h->prof_ev.size()) {
       for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_ev.push_back(e); }
     }
@@ -188,12 +320,19 @@ void launch_spmm(cs_b200_handle* h, const T* X, T* Y, const T* B) {
     e1 = h->prof_ev[h->prof_used++];
     cudaEventRecord(e0, h->stream);
   }
-  k_spmm<T, KT, MODE><<<grid, NT, 0, h->stream>>>(h->d_rowptr, h->d_colidx, (const T*)h->d_vals,
-                                                  h->d_bstart, h->nblocks, X, Y, B, h->d_ctl,
-                                                  h->d_partials);
-  if (h->profile) cudaEventRecord(e1, h->stream);
+  const SpmmEpi<T> ep{B, dinv, (T)omega, h->d_ctl, h->d_partials};
+  if (m.lpr == 4 && KT * 4 <= 32)
+    k_spmm<T, KT, MODE, (KT * 4 <= 32 ? 4 : 1)><<<grid, NT, 0, h->stream>>>(view<T>(m), X, Y, ep);
+  else
+    k_spmm<T, KT, MODE, 1><<<grid, NT, 0, h->stream>>>(view<T>(m), X, Y, ep);
+  if (prof) cudaEventRecord(e1, h->stream);
   h->stats.kernel_launches++;
-  h->stats.spmm_launches++;
+  if (timed) h->stats.spmm_launches++;
+}
+
+template <typename T, int KT, int MODE>
+void launch_spmm(cs_b200_handle* h, const T* X, T* Y, const T* B) {
+  launch_spmm_on<T, KT, MODE>(h, h->A0, X, Y, B, (const T*)h->d_dinv, 0.0, true);
 }
 
 // after a stream sync: fold the recorded SpMM event pairs into the profile totals
@@ -216,15 +355,65 @@ int ew_grid(cs_b200_handle* h) {
 }
 
 template <typename T, int KT>
+int ew_grid_n(cs_b200_handle* h, int64_t n_pad) {
+  const size_t nelem = (size_t)n_pad * KT;
+  const size_t per = (size_t)NT * Vec<T>::N;
+  return (int)std::max<size_t>(1, std::min<size_t>(h->grid_ew, (nelem + per - 1) / per));
+}
+
+// z = M^-1 r : one V(1,1) cycle, damped Jacobi, on panels of width KT.
+//   in : h->R (residual, read-only)      out: h->Z ; rho_new = r.z folded into the last kernel
+// Level buffers: b = right-hand side, x = running correction, t = residual scratch,
+// y = post-smoothed correction.  Finest level: b = R, x = stage, t = AP, y = Z.
+template <typename T, int KT>
+void launch_vcycle(cs_b200_handle* h) {
+  const int nl = (int)h->lv.size();
+  auto B = [&](int l) { return l == 0 ? (T*)h->R : (T*)h->lv[l].b; };
+  auto X = [&](int l) { return l == 0 ? (T*)h->stage : (T*)h->lv[l].x; };
+  auto Tm = [&](int l) { return l == 0 ? (T*)h->AP : (T*)h->lv[l].t; };
+  auto Y = [&](int l) { return l == 0 ? (T*)h->Z : (T*)h->lv[l].y; };
+  for (int l = 0; l < nl - 1; ++l) {
+    DevLevel& L = h->lv[l];
+    const size_t nelem = (size_t)L.n_pad * KT;
+    k_jacobi0<T, KT><<<ew_grid_n<T, KT>(h, L.n_pad), NT, 0, h->stream>>>(
+        nelem, B(l), (const T*)L.dinv, (T)L.omega, X(l));
+    h->stats.kernel_launches++;
+    launch_spmm_on<T, KT, SP_RES>(h, L.A, X(l), Tm(l), B(l), nullptr, 0.0, l == 0);
+    launch_spmm_on<T, KT, SP_PLAIN>(h, L.R, Tm(l), B(l + 1), nullptr, nullptr, 0.0, false);
+  }
+  {
+    DevLevel& C = h->lv[nl - 1];
+    k_coarse_dense<T, KT><<<1, NT, 0, h->stream>>>((int)C.n, h->d_pinv, (const T*)B(nl - 1), Y(nl - 1));
+    h->stats.kernel_launches++;
+  }
+  for (int l = nl - 2; l >= 0; --l) {
+    DevLevel& L = h->lv[l];
+    launch_spmm_on<T, KT, SP_ADD>(h, L.P, Y(l + 1), X(l), nullptr, nullptr, 0.0, false);
+    if (l == 0)
+      launch_spmm_on<T, KT, SP_JACOBI_DOT>(h, L.A, X(l), Y(l), B(l), (const T*)L.dinv, L.omega, true);
+    else
+      launch_spmm_on<T, KT, SP_JACOBI>(h, L.A, X(l), Y(l), B(l), (const T*)L.dinv, L.omega, false);
+  }
+}
+
+template <typename T, int KT>
 void launch_iteration(cs_b200_handle* h) {
   const size_t nelem = (size_t)h->n_pad * KT;
   const int g = ew_grid<T, KT>(h);
-  launch_spmm<T, KT, 1>(h, (const T*)h->P, (T*)h->AP, nullptr);
-  k_cg_update_r<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->AP, (const T*)h->d_dinv,
-                                                (T*)h->R, h->d_ctl, h->d_partials);
-  k_cg_update_xp<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->R, (const T*)h->d_dinv,
-                                                 (T*)h->X, (T*)h->P, h->d_ctl);
-  h->stats.kernel_launches += 2;
+  launch_spmm<T, KT, SP_CG>(h, (const T*)h->P, (T*)h->AP, nullptr);
+  if (!h->amg) {
+    k_cg_update_r<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->AP, (const T*)h->d_dinv,
+                                                  (T*)h->R, h->d_ctl, h->d_partials);
+    k_cg_update_xp<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->R, (const T*)h->d_dinv,
+                                                   (T*)h->X, (T*)h->P, h->d_ctl);
+    h->stats.kernel_launches += 2;
+  } else {
+    k_cg_update_xr<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->P, (const T*)h->AP, (T*)h->X,
+                                                   (T*)h->R, h->d_ctl);
+    launch_vcycle<T, KT>(h);
+    k_cg_update_p<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->P, h->d_ctl);
+    h->stats.kernel_launches += 2;
+  }
 }
 
 template <typename T, int KT>
@@ -239,6 +428,8 @@ int run_chunk(cs_b200_handle* h, int chunk) {
       CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       for (int i = 0; i < chunk; ++i) launch_iteration<T, KT>(h);
       CK(h, cudaStreamEndCapture(h->stream, &graph));
+      gs.kernels = h->stats.kernel_launches - kl;
+      gs.spmms = h->stats.spmm_launches - sl;
       h->stats.kernel_launches = kl;
       h->stats.spmm_launches = sl;
       CK(h, cudaGraphInstantiate(&gs.exec, graph, 0));
@@ -246,8 +437,8 @@ int run_chunk(cs_b200_handle* h, int chunk) {
       gs.chunk = chunk;
     }
     CK(h, cudaGraphLaunch(gs.exec, h->stream));
-    h->stats.kernel_launches += 3 * (int64_t)chunk;
-    h->stats.spmm_launches += chunk;
+    h->stats.kernel_launches += gs.kernels;
+    h->stats.spmm_launches += gs.spmms;
   } else {
     for (int i = 0; i < chunk; ++i) launch_iteration<T, KT>(h);
     CK(h, cudaGetLastError());
@@ -268,12 +459,24 @@ int solve_panel(cs_b200_handle* h, double rtol, int64_t itmax) {
   const int g = ew_grid<T, KT>(h);
   const int imax = (int)std::min<int64_t>(itmax, std::numeric_limits<int>::max() - 1);
   CK(h, cudaEventRecord(h->ev2, h->stream));
-  k_cg_init<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->B, (const T*)h->d_dinv, (T*)h->X,
-                                            (T*)h->R, (T*)h->P, h->d_ctl, h->d_partials, rtol, atol,
-                                            imax);
-  h->stats.kernel_launches++;
+  if (!h->amg) {
+    k_cg_init<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->B, (const T*)h->d_dinv, (T*)h->X,
+                                              (T*)h->R, (T*)h->P, h->d_ctl, h->d_partials, rtol, atol,
+                                              imax);
+    h->stats.kernel_launches++;
+  } else {
+    // x = 0, p = 0, r = b ; z = M^-1 r (V-cycle; its last kernel sets rho0, tolerances,
+    // activity because ctl->init = 1) ; p = z + 0*p
+    CK(h, cudaMemsetAsync(h->X, 0, nelem * sizeof(T), h->stream));
+    CK(h, cudaMemsetAsync(h->P, 0, nelem * sizeof(T), h->stream));
+    CK(h, cudaMemcpyAsync(h->R, h->B, nelem * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    k_set_ctl<<<1, 1, 0, h->stream>>>(h->d_ctl, rtol, atol, imax);
+    launch_vcycle<T, KT>(h);
+    k_cg_update_p<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->P, h->d_ctl);
+    h->stats.kernel_launches += 2;
+  }
   CK(h, cudaGetLastError());
-  const int chunk = h->opts.check_every;
+  const int chunk = h->amg ? std::min(h->opts.check_every, 4) : h->opts.check_every;
   for (;;) {
     CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PanelCtl), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
@@ -546,7 +749,8 @@ int cs_b200_create(int64_t n, int64_t nnz, const void* rowptr, const void* colid
   CKC(cudaMemcpyAsync(h->d_rowptr, rp.data(), (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CKC(cudaMemcpyAsync(h->d_colidx, ci.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CKC(cudaMemcpyAsync(h->d_vals, vals, (size_t)nnz * es, cudaMemcpyHostToDevice, h->stream));
-  rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp) : finish_setup<float>(h, rp);
+  rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, &ci, (const double*)vals)
+                            : finish_setup<float>(h, rp, &ci, (const float*)vals);
   if (rc) return fail(rc);
   cudaEventRecord(h->ev1, h->stream);
   cudaEventSynchronize(h->ev1);
@@ -580,7 +784,8 @@ int cs_b200_create_from_device(int64_t n, int64_t nnz, const int32_t* d_rowptr,
     set_err(h, CS_B200_ERR_CUDA, "CUDA error %s reading rowptr", cudaGetErrorString(e));
     g_create_error = h->err; cs_b200_destroy(h); return CS_B200_ERR_CUDA;
   }
-  rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp) : finish_setup<float>(h, rp);
+  rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, nullptr, (const double*)nullptr)
+                            : finish_setup<float>(h, rp, nullptr, (const float*)nullptr);
   if (rc) { g_create_error = h->err; cs_b200_destroy(h); return rc; }
   cudaEventRecord(h->ev1, h->stream);
   cudaEventSynchronize(h->ev1);
@@ -597,6 +802,17 @@ void cs_b200_destroy(cs_b200_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->owns_matrix) { cudaFree(h->d_rowptr); cudaFree(h->d_colidx); cudaFree(h->d_vals); }
+  for (size_t l = 0; l < h->lv.size(); ++l) {
+    DevLevel& L = h->lv[l];
+    if (l > 0) {
+      free_csr(L.A);
+      cudaFree(L.dinv); cudaFree(L.x); cudaFree(L.b); cudaFree(L.t); cudaFree(L.y);
+    }
+    free_csr(L.P);
+    free_csr(L.R);
+  }
+  cudaFree(h->Z);
+  cudaFree(h->d_pinv);
   void* bufs[] = {h->d_dinv, h->d_bstart, h->X, h->R, h->P, h->AP, h->B, h->stage,
                   h->d_cum, h->d_max, h->d_ctl, h->d_partials, h->d_flush};
   for (void* b : bufs) if (b) cudaFree(b);

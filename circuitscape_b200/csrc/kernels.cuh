@@ -43,6 +43,8 @@ struct PanelCtl {
   int itmax;
   int nactive;
   unsigned int ticket;    // last-CTA-done counter (self-resetting)
+  int init;               // AMG path: 1 while the first z = M^-1 r is being formed
+  double rtol, atol;      // stop-test parameters (AMG path reads them on the device)
 };
 
 // ---------------------------------------------------------------------------
@@ -172,78 +174,166 @@ __device__ __forceinline__ bool grid_reduce(double (&val)[NV][VEC], double* part
   return true;
 }
 
+// CG bookkeeping after z = M^-1 r and rho_new[c] = r.z are known (general preconditioner).
+// First call of a solve (ctl->init): thresholds and activity; later: beta, stop test, freeze.
+template <int KT>
+__device__ __forceinline__ void cg_after_precond(PanelCtl* ctl, const double* rho_new) {
+  const int c = threadIdx.x;
+  const int init = ctl->init;
+  const int it = ctl->iter + 1;
+  __syncthreads();
+  if (c < KT) {
+    const double rn = fabs(rho_new[c]);
+    if (init) {
+      const double tol = ctl->atol + ctl->rtol * sqrt(rn);
+      ctl->rho[c] = rn;
+      ctl->rho0[c] = rn;
+      ctl->tol[c] = tol;
+      ctl->active[c] = (rn > 0.0 && sqrt(rn) > tol && ctl->itmax > 0) ? 1 : 0;
+      ctl->iters[c] = 0;
+      ctl->alpha[c] = 0.0;
+      ctl->beta[c] = 0.0;
+    } else if (ctl->active[c]) {
+      const double ro = ctl->rho[c];
+      ctl->beta[c] = ro > 0.0 ? rn / ro : 0.0;
+      ctl->rho[c] = rn;
+      ctl->iters[c] = it;
+      if (!(sqrt(rn) > ctl->tol[c]) || it >= ctl->itmax) ctl->active[c] = 0;
+    } else {
+      ctl->beta[c] = 0.0;
+    }
+  }
+  __syncthreads();
+  if (c == 0) {
+    int na = 0;
+    for (int k = 0; k < KT; ++k) na += ctl->active[k];
+    ctl->nactive = na;
+    ctl->iter = init ? 0 : it;
+    ctl->init = 0;
+  }
+}
+
 #define CSB_REDUCE_SMEM(NV, KT)                         \
   __shared__ double s_warp[NWARP * (NV) * (KT)];        \
   __shared__ double s_tree[NT];                         \
   __shared__ double s_out[(NV) * (KT)];
 
 // ---------------------------------------------------------------------------
-// SpMM  Y = A X  on an n x KT panel, CSR "row-block streaming":
+// SpMM  Y = op(A X)  on an n x KT panel, CSR "row-block streaming":
 //   a CTA takes a block of consecutive rows whose nnz fit NNZ_CAP, streams that
 //   contiguous slice of vals/colidx into shared memory with coalesced loads, then
-//   thread (row_local, c) walks its row out of shared memory and gathers X[col][c]
+//   LPR lanes per (row, c) walk the row out of shared memory and gather X[col][c]
 //   (KT lanes read KT*sizeof(T) contiguous bytes; for the raster stencil the columns
 //   of neighbouring rows are neighbouring -> sectors are shared across the warp).
-// MODE 0: plain.  MODE 1: CG -- also dot(X, Y) per column; last CTA sets alpha.
-// MODE 2: residual  Y = B - A X  with ||Y||^2 and ||B||^2 per column.
+// The same kernel serves the operator of every multigrid level, the prolongators
+// and the restrictions; the epilogue (MODE) fuses what follows the product:
+//   SP_PLAIN       Y = A X
+//   SP_CG          Y = A X ; dot(X, Y) per column ; last CTA: alpha = rho / pAp
+//   SP_RESNORM     Y = B - A X ; ||Y||^2, ||B||^2 per column      (true-residual gate)
+//   SP_RES         Y = B - A X
+//   SP_JACOBI      Y = X + omega Dinv (B - A X)                    (damped-Jacobi sweep)
+//   SP_JACOBI_DOT  same ; dot(B, Y) per column ; last CTA: CG beta / stop test
+//                  (B = r, Y = z = M^-1 r: the last kernel of the V-cycle)
+//   SP_ADD         Y += A X                                        (prolongate + correct)
 // A row longer than NNZ_CAP (polygon hub / power-law node) is its own block and is
 // reduced by the whole CTA.
 // ---------------------------------------------------------------------------
-template <typename T, int KT, int MODE>
+enum { SP_PLAIN = 0, SP_CG = 1, SP_RESNORM = 2, SP_RES = 3, SP_JACOBI = 4, SP_JACOBI_DOT = 5, SP_ADD = 6 };
+
+template <typename T> struct CsrDev {
+  const int* rowptr;
+  const int* colidx;
+  const T* vals;
+  const int* bstart;   // row-block starts (nblocks + 1)
+  int nblocks;
+  int nrows;
+};
+
+template <typename T> struct SpmmEpi {
+  const T* B;
+  const T* dinv;
+  T omega;
+  PanelCtl* ctl;
+  double* partials;
+};
+
+template <typename T, int MODE>
+__device__ __forceinline__ void spmm_epilogue(int row, size_t o, T acc, const T* __restrict__ X,
+                                              T* __restrict__ Y, const SpmmEpi<T>& ep, double& dot0,
+                                              double& dot1) {
+  if (MODE == SP_PLAIN) {
+    Y[o] = acc;
+  } else if (MODE == SP_CG) {
+    Y[o] = acc;
+    dot0 += (double)acc * (double)X[o];
+  } else if (MODE == SP_RESNORM) {
+    const T bb = ep.B[o];
+    const T rr = bb - acc;
+    Y[o] = rr;
+    dot0 += (double)rr * (double)rr;
+    dot1 += (double)bb * (double)bb;
+  } else if (MODE == SP_RES) {
+    Y[o] = ep.B[o] - acc;
+  } else if (MODE == SP_JACOBI || MODE == SP_JACOBI_DOT) {
+    const T bb = ep.B[o];
+    const T yn = X[o] + ep.omega * ep.dinv[row] * (bb - acc);
+    Y[o] = yn;
+    if (MODE == SP_JACOBI_DOT) dot0 += (double)bb * (double)yn;
+  } else {
+    Y[o] += acc;
+  }
+}
+
+template <typename T, int KT, int MODE, int LPR>
 __global__ void __launch_bounds__(NT)
-k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const T* __restrict__ vals,
-       const int* __restrict__ bstart, int nblocks, const T* __restrict__ X, T* __restrict__ Y,
-       const T* __restrict__ B, PanelCtl* ctl, double* partials) {
+k_spmm(const CsrDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
   __shared__ T s_val[NNZ_CAP];
   __shared__ int s_col[NNZ_CAP];
   __shared__ double s_long[NT];
   const int tid = threadIdx.x;
   const int c = tid % KT;
-  constexpr int RPP = NT / KT;  // rows per pass
+  const int lr = (tid / KT) % LPR;          // lane within the row
+  constexpr int RPP = NT / (KT * LPR);      // rows per pass
   double dot0 = 0.0, dot1 = 0.0;
 
-  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-    const int r0 = bstart[blk], r1 = bstart[blk + 1];
-    const int s = rowptr[r0], e = rowptr[r1];
+  for (int blk = blockIdx.x; blk < A.nblocks; blk += gridDim.x) {
+    const int r0 = A.bstart[blk], r1 = A.bstart[blk + 1];
+    const int s = A.rowptr[r0], e = A.rowptr[r1];
     const int cnt = e - s;
     __syncthreads();
     if (cnt <= NNZ_CAP) {
       for (int i = tid; i < cnt; i += NT) {
-        s_val[i] = ld_stream(vals + s + i);
-        s_col[i] = ld_stream(colidx + s + i);
+        s_val[i] = ld_stream(A.vals + s + i);
+        s_col[i] = ld_stream(A.colidx + s + i);
       }
       __syncthreads();
-      for (int rl = tid / KT; rl < r1 - r0; rl += RPP) {
+      const int nr = r1 - r0;
+      for (int base = 0; base < nr; base += RPP) {      // uniform trip count: shuffles below
+        const int rl = base + tid / (KT * LPR);
+        const bool valid = rl < nr;
         const int row = r0 + rl;
-        const int a = rowptr[row] - s, b = rowptr[row + 1] - s;
         T acc = T(0);
-        for (int j = a; j < b; ++j) acc += s_val[j] * X[(size_t)s_col[j] * KT + c];
-        const size_t o = (size_t)row * KT + c;
-        if (MODE == 0) {
-          Y[o] = acc;
-        } else if (MODE == 1) {
-          Y[o] = acc;
-          dot0 += (double)acc * (double)X[o];
-        } else {
-          const T bb = B[o];
-          const T rr = bb - acc;
-          Y[o] = rr;
-          dot0 += (double)rr * (double)rr;
-          dot1 += (double)bb * (double)bb;
+        if (valid) {
+          const int a = A.rowptr[row] - s, b = A.rowptr[row + 1] - s;
+          for (int j = a + lr; j < b; j += LPR) acc += s_val[j] * X[(size_t)s_col[j] * KT + c];
         }
+#pragma unroll
+        for (int off = KT; off < KT * LPR; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (valid && lr == 0) spmm_epilogue<T, MODE>(row, (size_t)row * KT + c, acc, X, Y, ep, dot0, dot1);
       }
     } else {
       const int row = r0;  // long row: r1 == r0 + 1
       double acc = 0.0;
+      constexpr int GRP = NT / KT;
       for (int base = 0; base < cnt; base += NNZ_CAP) {
         const int m = min(NNZ_CAP, cnt - base);
         __syncthreads();
         for (int i = tid; i < m; i += NT) {
-          s_val[i] = ld_stream(vals + s + base + i);
-          s_col[i] = ld_stream(colidx + s + base + i);
+          s_val[i] = ld_stream(A.vals + s + base + i);
+          s_col[i] = ld_stream(A.colidx + s + base + i);
         }
         __syncthreads();
-        for (int j = tid / KT; j < m; j += RPP)
+        for (int j = tid / KT; j < m; j += GRP)
           acc += (double)s_val[j] * (double)X[(size_t)s_col[j] * KT + c];
       }
       __syncthreads();
@@ -251,43 +341,35 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const T* 
       __syncthreads();
       if (tid < KT) {
         double t = 0.0;
-        for (int g = 0; g < RPP; ++g) t += s_long[g * KT + tid];
-        const size_t o = (size_t)row * KT + tid;
-        const T accT = (T)t;
-        if (MODE == 0) {
-          Y[o] = accT;
-        } else if (MODE == 1) {
-          Y[o] = accT;
-          dot0 += (double)accT * (double)X[o];
-        } else {
-          const T bb = B[o];
-          const T rr = bb - accT;
-          Y[o] = rr;
-          dot0 += (double)rr * (double)rr;
-          dot1 += (double)bb * (double)bb;
-        }
+        for (int g = 0; g < GRP; ++g) t += s_long[g * KT + tid];
+        spmm_epilogue<T, MODE>(row, (size_t)row * KT + tid, (T)t, X, Y, ep, dot0, dot1);
       }
     }
   }
-  if (MODE == 1) {
+  if (MODE == SP_CG) {
     CSB_REDUCE_SMEM(1, KT)
     double v[1][1] = {{dot0}};
-    if (grid_reduce<KT, 1, 1, false>(v, partials, &ctl->ticket, s_warp, s_tree, s_out)) {
+    if (grid_reduce<KT, 1, 1, false>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
       if (tid < KT) {
         const double pap = s_out[tid];
-        ctl->pap[tid] = pap;
-        ctl->alpha[tid] = (ctl->active[tid] && pap > 0.0) ? ctl->rho[tid] / pap : 0.0;
+        ep.ctl->pap[tid] = pap;
+        ep.ctl->alpha[tid] = (ep.ctl->active[tid] && pap > 0.0) ? ep.ctl->rho[tid] / pap : 0.0;
       }
     }
-  } else if (MODE == 2) {
+  } else if (MODE == SP_RESNORM) {
     CSB_REDUCE_SMEM(2, KT)
     double v[2][1] = {{dot0}, {dot1}};
-    if (grid_reduce<KT, 1, 2, false>(v, partials, &ctl->ticket, s_warp, s_tree, s_out)) {
+    if (grid_reduce<KT, 1, 2, false>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
       if (tid < KT) {
-        ctl->resid[tid] = s_out[tid];
-        ctl->bnorm[tid] = s_out[KT + tid];
+        ep.ctl->resid[tid] = s_out[tid];
+        ep.ctl->bnorm[tid] = s_out[KT + tid];
       }
     }
+  } else if (MODE == SP_JACOBI_DOT) {
+    CSB_REDUCE_SMEM(1, KT)
+    double v[1][1] = {{dot0}};
+    if (grid_reduce<KT, 1, 1, false>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out))
+      cg_after_precond<KT>(ep.ctl, s_out);
   }
 }
 
@@ -426,6 +508,82 @@ k_cg_update_xp(size_t nelem, const T* __restrict__ R, const T* __restrict__ dinv
     }
     vstore(X + e, x);
     vstore(P + e, p);
+  }
+}
+
+// AMG-PCG:  X += alpha*P ;  R -= alpha*AP   (z and rho come from the V-cycle)
+template <typename T, int KT>
+__global__ void __launch_bounds__(NT)
+k_cg_update_xr(size_t nelem, const T* __restrict__ P, const T* __restrict__ AP, T* __restrict__ X,
+               T* __restrict__ R, const PanelCtl* ctl) {
+  constexpr int VEC = Vec<T>::N;
+  const size_t e0 = ((size_t)blockIdx.x * NT + threadIdx.x) * VEC;
+  const size_t stride = (size_t)gridDim.x * NT * VEC;
+  T al[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) al[i] = (T)ctl->alpha[(e0 + i) % KT];
+  for (size_t e = e0; e < nelem; e += stride) {
+    T p[VEC], ap[VEC], x[VEC], r[VEC];
+    vload(P + e, p);
+    vload(AP + e, ap);
+    vload(X + e, x);
+    vload(R + e, r);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      x[i] += al[i] * p[i];
+      r[i] -= al[i] * ap[i];
+    }
+    vstore(X + e, x);
+    vstore(R + e, r);
+  }
+}
+
+// AMG-PCG:  P = Z + beta*P
+template <typename T, int KT>
+__global__ void __launch_bounds__(NT)
+k_cg_update_p(size_t nelem, const T* __restrict__ Z, T* __restrict__ P, const PanelCtl* ctl) {
+  constexpr int VEC = Vec<T>::N;
+  const size_t e0 = ((size_t)blockIdx.x * NT + threadIdx.x) * VEC;
+  const size_t stride = (size_t)gridDim.x * NT * VEC;
+  T be[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) be[i] = (T)ctl->beta[(e0 + i) % KT];
+  for (size_t e = e0; e < nelem; e += stride) {
+    T z[VEC], p[VEC];
+    vload(Z + e, z);
+    vload(P + e, p);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p[i] = z[i] + be[i] * p[i];
+    vstore(P + e, p);
+  }
+}
+
+// first (zero-guess) damped-Jacobi sweep of a level:  X = omega * Dinv * B
+template <typename T, int KT>
+__global__ void __launch_bounds__(NT)
+k_jacobi0(size_t nelem, const T* __restrict__ B, const T* __restrict__ dinv, T omega,
+          T* __restrict__ X) {
+  constexpr int VEC = Vec<T>::N;
+  constexpr int L = Log2<KT>::v;
+  const size_t stride = (size_t)gridDim.x * NT * VEC;
+  for (size_t e = ((size_t)blockIdx.x * NT + threadIdx.x) * VEC; e < nelem; e += stride) {
+    T b[VEC], x[VEC];
+    vload(B + e, b);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) x[i] = omega * dinv[(e + i) >> L] * b[i];
+    vstore(X + e, x);
+  }
+}
+
+// coarsest level:  X = Pinv * B  (dense n x n pseudo-inverse in double, one CTA)
+template <typename T, int KT>
+__global__ void __launch_bounds__(NT)
+k_coarse_dense(int n, const double* __restrict__ pinv, const T* __restrict__ B, T* __restrict__ X) {
+  for (int e = threadIdx.x; e < n * KT; e += NT) {
+    const int i = e / KT, c = e % KT;
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) acc += pinv[(size_t)i * n + j] * (double)B[(size_t)j * KT + c];
+    X[e] = (T)acc;
   }
 }
 
@@ -582,6 +740,14 @@ k_cur_acc(int n, const int* __restrict__ rowptr, const int* __restrict__ colidx,
       }
     }
   }
+}
+
+__global__ void k_set_ctl(PanelCtl* ctl, double rtol, double atol, int itmax) {
+  ctl->rtol = rtol;
+  ctl->atol = atol;
+  ctl->itmax = itmax;
+  ctl->init = 1;
+  ctl->iter = 0;
 }
 
 template <typename T>

@@ -1,0 +1,138 @@
+"""The host-side smoothed-aggregation setup (circuitscape_b200/csrc/amg_host.hpp),
+checked without a GPU: Galerkin identities of the hierarchy and convergence of the
+Jacobi-smoothed V(1,1)-PCG it defines (the same cycle the device runs)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from circuitscape_b200 import graph
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("amgh") / "libamgh.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(HERE, "amg_host_harness.cpp")])
+    lib = C.CDLL(so)
+    lib.amgh_build.restype = C.c_void_p
+    lib.amgh_build.argtypes = [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.amgh_nlevels.argtypes = [C.c_void_p]
+    lib.amgh_dims.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
+    lib.amgh_copy.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.amgh_pinv.argtypes = [C.c_void_p, C.c_void_p]
+    lib.amgh_free.argtypes = [C.c_void_p]
+    return lib
+
+
+def build(lib, A):
+    A = sp.csr_matrix(A, dtype=np.float64)
+    A.sort_indices()
+    ptr = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    idx = np.ascontiguousarray(A.indices, dtype=np.int32)
+    val = np.ascontiguousarray(A.data)
+    h = lib.amgh_build(A.shape[0], A.nnz, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data)
+    levels = []
+    for l in range(lib.amgh_nlevels(h)):
+        mats = []
+        for which in range(3):
+            nr, nc, nnz = C.c_long(), C.c_long(), C.c_long()
+            om = C.c_double()
+            lib.amgh_dims(h, l, which, C.byref(nr), C.byref(nc), C.byref(nnz), C.byref(om))
+            if nr.value == 0:
+                mats.append(None)
+                continue
+            p = np.zeros(nr.value + 1, dtype=np.int32)
+            i = np.zeros(nnz.value, dtype=np.int32)
+            v = np.zeros(nnz.value)
+            lib.amgh_copy(h, l, which, p.ctypes.data, i.ctypes.data, v.ctypes.data)
+            mats.append(sp.csr_matrix((v, i, p), shape=(nr.value, nc.value)))
+        levels.append(dict(A=mats[0], P=mats[1], R=mats[2], omega=om.value))
+    nc = levels[-1]["A"].shape[0]
+    pinv = np.zeros((nc, nc))
+    lib.amgh_pinv(h, pinv.ctypes.data)
+    lib.amgh_free(h)
+    return levels, pinv
+
+
+def vcycle(levels, pinv, b, l=0):
+    if l == len(levels) - 1:
+        return pinv @ b
+    L = levels[l]
+    A = L["A"]
+    dinv = 1.0 / A.diagonal()
+    x = L["omega"] * dinv * b
+    r = b - A @ x
+    x = x + L["P"] @ vcycle(levels, pinv, L["R"] @ r, l + 1)
+    return x + L["omega"] * dinv * (b - A @ x)
+
+
+def pcg(A, b, M, rtol=1e-6, itmax=500):
+    x = np.zeros_like(b); r = b.copy(); z = M(r); p = z.copy(); g = r @ z
+    eps = 1.5e-8 + rtol * np.sqrt(g); it = 0
+    while np.sqrt(abs(g)) > eps and it < itmax:
+        Ap = A @ p; a = g / (p @ Ap); x += a * p; r -= a * Ap
+        z = M(r); gn = r @ z; p = z + (gn / g) * p; g = gn; it += 1
+    return x, it
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lognormal_holes"])
+def test_hierarchy_and_convergence(harness, kind):
+    if kind == "uniform":
+        A, _ = graph.synthetic_raster_laplacian(120, 90, seed=1)
+    else:
+        rng = np.random.default_rng(2)
+        g = 1.0 / np.exp(rng.normal(0, 1.5, (120, 90)))
+        g[rng.random(g.shape) < 0.05] = 0
+        nm = graph.construct_node_map(g)
+        G = graph.laplacian(graph.construct_graph(g, nm, False, False))
+        big = max(graph.connected_components(G), key=len) - 1
+        A = G[big][:, big].tocsr()
+    levels, pinv = build(harness, A)
+    assert len(levels) >= 3 and levels[-1]["A"].shape[0] <= 96
+    opc = sum(l["A"].nnz for l in levels) / A.nnz
+    assert opc < 1.6
+    for l in range(len(levels) - 1):
+        L = levels[l]
+        assert abs(L["R"] - L["P"].T).max() < 1e-15
+        Ac = (L["R"] @ L["A"] @ L["P"]).tocsr()
+        assert abs(Ac - levels[l + 1]["A"]).max() < 1e-12 * abs(Ac).max()
+        # constants stay in the (near) null space:  A_c (P^T-consistent candidate) ~ 0
+        assert np.abs(L["A"] @ np.ones(L["A"].shape[0])).max() < 1e-9 if l == 0 else True
+    Ac = levels[-1]["A"].toarray()
+    assert np.abs(Ac @ pinv @ Ac - Ac).max() < 1e-9 * np.abs(Ac).max()
+    n = A.shape[0]
+    b = np.zeros(n); b[3] = -1.0; b[n - 5] = 1.0
+    x, it = pcg(A, b, lambda r: vcycle(levels, pinv, r))
+    assert it <= 30, it
+    assert np.linalg.norm(A @ x - b) / np.sqrt(2) < 1e-4
+    import scipy.sparse.linalg as spla
+    keep = np.arange(1, n)
+    xr = np.zeros(n); xr[1:] = spla.splu(A[keep][:, keep].tocsc()).solve(b[1:])
+    Rr = xr[n - 5] - xr[3]
+    assert abs((x[n - 5] - x[3]) - Rr) / Rr < 1e-6
+
+
+def test_spd_with_grounds_and_hub(harness):
+    rng = np.random.default_rng(5)
+    n = 4000
+    rows = np.repeat(np.arange(3, n), 3)
+    cols = (rng.random(rows.size) ** 2 * rows).astype(np.int64)
+    rows = np.concatenate([rows, np.zeros(600, dtype=np.int64)])
+    cols = np.concatenate([cols, np.arange(1, 601)])
+    keep = rows != cols
+    W = sp.coo_matrix((rng.uniform(0.1, 1, keep.sum()), (rows[keep], cols[keep])), shape=(n, n)).tocsr()
+    A = graph.laplacian(W + W.T)
+    g = np.zeros(n); g[10] = 2.0
+    M = (A + sp.diags(g)).tocsr()
+    levels, pinv = build(harness, M)
+    b = rng.standard_normal(n)
+    x, it = pcg(M, b, lambda r: vcycle(levels, pinv, r), rtol=1e-8)
+    assert it <= 60, it
+    assert np.linalg.norm(M @ x - b) / np.linalg.norm(b) < 1e-6
