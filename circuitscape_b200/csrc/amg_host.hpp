@@ -277,7 +277,9 @@ inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 9
     h.levels.emplace_back();
     h.levels.back().A = std::move(Ac);
   }
-  h.coarse_pinv = dense_pinv(h.levels.back().A);
+  // exact coarse solve only while the dense eigen-solve stays cheap; otherwise (coarsening
+  // stalled on an irregular graph) the device falls back to a few Jacobi sweeps there
+  if (h.levels.back().A.nrows <= 320) h.coarse_pinv = dense_pinv(h.levels.back().A);
   return h;
 }
 

@@ -201,8 +201,10 @@ int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<i
     }
   }
   const size_t nc = (size_t)hier.levels.back().A.nrows;
-  CK(h, cudaMalloc(&h->d_pinv, std::max<size_t>(1, nc * nc) * sizeof(double)));
-  CK(h, cudaMemcpy(h->d_pinv, hier.coarse_pinv.data(), nc * nc * sizeof(double), cudaMemcpyHostToDevice));
+  if (hier.coarse_pinv.size() == nc * nc && nc > 0) {
+    CK(h, cudaMalloc(&h->d_pinv, nc * nc * sizeof(double)));
+    CK(h, cudaMemcpy(h->d_pinv, hier.coarse_pinv.data(), nc * nc * sizeof(double), cudaMemcpyHostToDevice));
+  }
   const size_t pe = (size_t)h->n_pad * h->ktmax * sizeof(T);
   CK(h, cudaMalloc(&h->Z, pe));
   CK(h, cudaMemset(h->Z, 0, pe));
@@ -279,7 +281,7 @@ int common_create(cs_b200_handle* h, const cs_b200_opts* opts) {
   cudaDeviceProp prop;
   CK(h, cudaGetDeviceProperties(&prop, h->device));
   h->num_sms = prop.multiProcessorCount;
-  h->grid_spmm = h->num_sms * 4;
+  h->grid_spmm = h->num_sms * 8;
   h->grid_ew = h->num_sms * 4;
   CK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(h, cudaEventCreate(&h->ev0));
@@ -383,8 +385,18 @@ void launch_vcycle(cs_b200_handle* h) {
   }
   {
     DevLevel& C = h->lv[nl - 1];
-    k_coarse_dense<T, KT><<<1, NT, 0, h->stream>>>((int)C.n, h->d_pinv, (const T*)B(nl - 1), Y(nl - 1));
-    h->stats.kernel_launches++;
+    if (h->d_pinv) {
+      k_coarse_dense<T, KT><<<1, NT, 0, h->stream>>>((int)C.n, h->d_pinv, (const T*)B(nl - 1), Y(nl - 1));
+      h->stats.kernel_launches++;
+    } else {  // coarsening stalled above the dense limit: 4 damped-Jacobi sweeps (symmetric)
+      const int l = nl - 1;
+      k_jacobi0<T, KT><<<ew_grid_n<T, KT>(h, C.n_pad), NT, 0, h->stream>>>(
+          (size_t)C.n_pad * KT, B(l), (const T*)C.dinv, (T)C.omega, X(l));
+      h->stats.kernel_launches++;
+      launch_spmm_on<T, KT, SP_JACOBI>(h, C.A, X(l), Y(l), B(l), (const T*)C.dinv, C.omega, false);
+      launch_spmm_on<T, KT, SP_JACOBI>(h, C.A, Y(l), X(l), B(l), (const T*)C.dinv, C.omega, false);
+      launch_spmm_on<T, KT, SP_JACOBI>(h, C.A, X(l), Y(l), B(l), (const T*)C.dinv, C.omega, false);
+    }
   }
   for (int l = nl - 2; l >= 0; --l) {
     DevLevel& L = h->lv[l];

@@ -302,24 +302,78 @@ k_spmm(const CsrDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const Spmm
     const int cnt = e - s;
     __syncthreads();
     if (cnt <= NNZ_CAP) {
-      for (int i = tid; i < cnt; i += NT) {
-        s_val[i] = ld_stream(A.vals + s + i);
-        s_col[i] = ld_stream(A.colidx + s + i);
-      }
-      __syncthreads();
-      const int nr = r1 - r0;
-      for (int base = 0; base < nr; base += RPP) {      // uniform trip count: shuffles below
-        const int rl = base + tid / (KT * LPR);
-        const bool valid = rl < nr;
-        const int row = r0 + rl;
-        T acc = T(0);
-        if (valid) {
-          const int a = A.rowptr[row] - s, b = A.rowptr[row + 1] - s;
-          for (int j = a + lr; j < b; j += LPR) acc += s_val[j] * X[(size_t)s_col[j] * KT + c];
-        }
+      constexpr int U = NNZ_CAP / NT;   // 9 matrix entries per thread per row block
+      if constexpr (KT == 1 && LPR == 1) {
+        // single right-hand side ("stream-gather"): thread i streams entry i of the block
+        // (coalesced vals/colidx), gathers x[col] and parks the PRODUCT in shared memory;
+        // all U entries' loads are issued before any use (U*2 streaming + U gather loads
+        // in flight per thread); then one thread per row sums its products.
+        T v[U];
+        int ci[U];
 #pragma unroll
-        for (int off = KT; off < KT * LPR; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (valid && lr == 0) spmm_epilogue<T, MODE>(row, (size_t)row * KT + c, acc, X, Y, ep, dot0, dot1);
+        for (int u = 0; u < U; ++u) {
+          const int i = tid + u * NT;
+          if (i < cnt) {
+            v[u] = ld_stream(A.vals + s + i);
+            ci[u] = ld_stream(A.colidx + s + i);
+          } else {
+            v[u] = T(0);
+            ci[u] = 0;
+          }
+        }
+        T xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = X[ci[u]];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = tid + u * NT;
+          if (i < cnt) s_val[i] = v[u] * xv[u];
+        }
+        __syncthreads();
+        const int row = r0 + tid;
+        if (row < r1) {
+          const int a = A.rowptr[row] - s, b = A.rowptr[row + 1] - s;
+          T acc = T(0);
+          for (int j = a; j < b; ++j) acc += s_val[j];
+          spmm_epilogue<T, MODE>(row, (size_t)row, acc, X, Y, ep, dot0, dot1);
+        }
+      } else {
+        {
+          T v[U];
+          int ci[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = tid + u * NT;
+            if (i < cnt) {
+              v[u] = ld_stream(A.vals + s + i);
+              ci[u] = ld_stream(A.colidx + s + i);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = tid + u * NT;
+            if (i < cnt) {
+              s_val[i] = v[u];
+              s_col[i] = ci[u];
+            }
+          }
+        }
+        __syncthreads();
+        const int nr = r1 - r0;
+        for (int base = 0; base < nr; base += RPP) {      // uniform trip count: shuffles below
+          const int rl = base + tid / (KT * LPR);
+          const bool valid = rl < nr;
+          const int row = r0 + rl;
+          T acc = T(0);
+          if (valid) {
+            const int a = A.rowptr[row] - s, b = A.rowptr[row + 1] - s;
+#pragma unroll 3
+            for (int j = a + lr; j < b; j += LPR) acc += s_val[j] * X[(size_t)s_col[j] * KT + c];
+          }
+#pragma unroll
+          for (int off = KT; off < KT * LPR; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          if (valid && lr == 0) spmm_epilogue<T, MODE>(row, (size_t)row * KT + c, acc, X, Y, ep, dot0, dot1);
+        }
       }
     } else {
       const int row = r0;  // long row: r1 == r0 + 1
