@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "amg_host.hpp"
+#include "win_host.hpp"
 #include "kernels.cuh"
 
 using namespace csb;
@@ -41,6 +42,12 @@ struct DevCsr {
   int nrows = 0;
   int64_t nnz = 0;
   int lpr = 1;  // lanes per row used by k_spmm for this matrix
+  // windowed row-block form for the TMA-staged kernel (win_host.hpp); null => plain kernel
+  WinMeta* win_meta = nullptr;
+  void* vals_p = nullptr;
+  unsigned short* lcol_p = nullptr;
+  unsigned short* roff_p = nullptr;
+  int64_t win_blocks = 0;
 };
 
 // one multigrid level below the finest (the finest level aliases the handle's own CSR)
@@ -131,9 +138,13 @@ void build_row_blocks(const std::vector<int>& rowptr, int64_t n, std::vector<int
   }
 }
 
+template <typename T>
+int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx,
+                   const std::vector<int>& bstart, int64_t ncols_pad);
+
 // upload one host CSR (double values) as a device CSR of T with its row blocks
 template <typename T>
-int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d) {
+int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowed) {
   d.nrows = (int)m.nrows;
   d.nnz = m.nnz();
   std::vector<int> bstart;
@@ -149,12 +160,50 @@ int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d) {
   CK(h, cudaMemcpy(d.colidx, m.idx.data(), (size_t)d.nnz * sizeof(int), cudaMemcpyHostToDevice));
   CK(h, cudaMemcpy(d.vals, v.data(), (size_t)d.nnz * sizeof(T), cudaMemcpyHostToDevice));
   CK(h, cudaMemcpy(d.bstart, bstart.data(), bstart.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (h->opts.window >= 0 && (h->opts.window > 0 || windowed)) {
+    const int64_t ncols_pad = (m.ncols + 3) / 4 * 4;
+    return build_windowed<T>(h, d, m.ptr.data(), m.idx.data(), bstart, ncols_pad);
+  }
   return CS_B200_OK;
+}
+
+void free_win(DevCsr& d) {
+  cudaFree(d.win_meta); cudaFree(d.vals_p); cudaFree(d.lcol_p); cudaFree(d.roff_p);
+  d.win_meta = nullptr; d.vals_p = nullptr; d.lcol_p = nullptr; d.roff_p = nullptr;
 }
 
 void free_csr(DevCsr& d) {
   cudaFree(d.rowptr); cudaFree(d.colidx); cudaFree(d.vals); cudaFree(d.bstart);
+  free_win(d);
   d = DevCsr{};
+}
+
+// Build + upload the windowed row-block form of a CSR already resident in `d`.
+// rowptr/colidx: host copies; ncols_pad: rows of the input panel (n_pad of the column space).
+template <typename T>
+int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx,
+                   const std::vector<int>& bstart, int64_t ncols_pad) {
+  static_assert(sizeof(WinMeta) == sizeof(csb_win::BlockMeta), "meta layout");
+  csb_win::Windowed w = csb_win::build(rowptr, colidx, bstart, ncols_pad);
+  d.win_blocks = w.windowed_blocks;
+  if (w.windowed_blocks == 0) return CS_B200_OK;   // nothing gained: keep the plain kernel
+  const size_t ne = w.lcol.size();
+  int* d_perm = nullptr;
+  CK(h, cudaMalloc(&d.win_meta, w.meta.size() * sizeof(WinMeta)));
+  CK(h, cudaMalloc(&d.vals_p, ne * sizeof(T)));
+  CK(h, cudaMalloc(&d.lcol_p, ne * sizeof(unsigned short)));
+  CK(h, cudaMalloc(&d.roff_p, w.roff.size() * sizeof(unsigned short)));
+  CK(h, cudaMalloc(&d_perm, ne * sizeof(int)));
+  CK(h, cudaMemcpy(d.win_meta, w.meta.data(), w.meta.size() * sizeof(WinMeta), cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(d.lcol_p, w.lcol.data(), ne * sizeof(unsigned short), cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(d.roff_p, w.roff.data(), w.roff.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(d_perm, w.perm_off.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
+  k_pack_vals<T><<<(int)std::min<size_t>(4096, (ne + 255) / 256), 256, 0, h->stream>>>(
+      ne, d_perm, (const T*)d.vals, (T*)d.vals_p);
+  CK(h, cudaGetLastError());
+  CK(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_perm);
+  return CS_B200_OK;
 }
 
 // Smoothed-aggregation hierarchy: built on the host (amg_host.hpp), resident on the device.
@@ -180,7 +229,7 @@ int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<i
       L.A = h->A0;  // alias, not owned
       L.dinv = h->d_dinv;
     } else {
-      int rc = upload_csr<T>(h, hl.A, L.A);
+      int rc = upload_csr<T>(h, hl.A, L.A, L.n >= 20000);
       if (rc) return rc;
       std::vector<T> dv(L.n_pad, T(0));
       for (int64_t i = 0; i < L.n; ++i) dv[i] = (T)hl.dinv[i];
@@ -194,9 +243,9 @@ int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<i
       }
     }
     if (l + 1 < nl) {
-      int rc = upload_csr<T>(h, hl.P, L.P);
+      int rc = upload_csr<T>(h, hl.P, L.P, L.n >= 20000);
       if (rc) return rc;
-      rc = upload_csr<T>(h, hl.R, L.R);
+      rc = upload_csr<T>(h, hl.R, L.R, L.n >= 20000);
       if (rc) return rc;
     }
   }
@@ -240,17 +289,25 @@ int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std:
       (int)h->n, (int)h->n_pad, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (T*)h->d_dinv);
   CK(h, cudaGetLastError());
   CK(h, cudaStreamSynchronize(h->stream));
-  if (h->opts.precond == CS_B200_PRECOND_AMG) {
-    std::vector<int> ci_local;
-    std::vector<T> v_local;
-    if (!h_colidx) {  // matrix arrived on the device (NCCL broadcast): fetch a host copy for setup
-      ci_local.resize(h->nnz);
+  std::vector<int> ci_local;
+  std::vector<T> v_local;
+  const bool want_win = h->opts.window >= 0 && (h->opts.window > 0 || h->n >= 20000);
+  const bool want_amg = h->opts.precond == CS_B200_PRECOND_AMG;
+  if (!h_colidx && (want_win || want_amg)) {  // matrix arrived on the device (NCCL broadcast)
+    ci_local.resize(h->nnz);
+    CK(h, cudaMemcpy(ci_local.data(), h->d_colidx, (size_t)h->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    h_colidx = &ci_local;
+    if (want_amg) {
       v_local.resize(h->nnz);
-      CK(h, cudaMemcpy(ci_local.data(), h->d_colidx, (size_t)h->nnz * sizeof(int), cudaMemcpyDeviceToHost));
       CK(h, cudaMemcpy(v_local.data(), h->d_vals, (size_t)h->nnz * sizeof(T), cudaMemcpyDeviceToHost));
-      h_colidx = &ci_local;
       h_vals = v_local.data();
     }
+  }
+  if (want_win) {
+    int rc = build_windowed<T>(h, h->A0, h_rowptr.data(), h_colidx->data(), bstart, h->n_pad);
+    if (rc) return rc;
+  }
+  if (want_amg) {
     int rc = setup_amg<T>(h, h_rowptr, *h_colidx, h_vals);
     if (rc) return rc;
   }
@@ -323,10 +380,26 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
     cudaEventRecord(e0, h->stream);
   }
   const SpmmEpi<T> ep{B, dinv, (T)omega, h->d_ctl, h->d_partials};
-  if (m.lpr == 4 && KT * 4 <= 32)
+  if (m.win_meta) {
+    const WinCsr<T> w{m.win_meta, (const T*)m.vals_p, m.lcol_p, m.roff_p, m.rowptr, m.colidx,
+                      (const T*)m.vals, m.nblocks};
+    const int wg = std::max(1, std::min(h->num_sms, m.nblocks));
+    constexpr int SMEM = WinSmem<T, KT, MODE>::TOTAL;
+    if (m.lpr == 4) {
+      constexpr int L4 = (KT * 4 <= 32 ? 4 : 1);
+      static bool once = false;
+      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, L4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
+      k_spmm_win<T, KT, MODE, L4><<<wg, WT, SMEM, h->stream>>>(w, X, Y, ep);
+    } else {
+      static bool once = false;
+      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
+      k_spmm_win<T, KT, MODE, 1><<<wg, WT, SMEM, h->stream>>>(w, X, Y, ep);
+    }
+  } else if (m.lpr == 4 && KT * 4 <= 32) {
     k_spmm<T, KT, MODE, (KT * 4 <= 32 ? 4 : 1)><<<grid, NT, 0, h->stream>>>(view<T>(m), X, Y, ep);
-  else
+  } else {
     k_spmm<T, KT, MODE, 1><<<grid, NT, 0, h->stream>>>(view<T>(m), X, Y, ep);
+  }
   if (prof) cudaEventRecord(e1, h->stream);
   h->stats.kernel_launches++;
   if (timed) h->stats.spmm_launches++;
@@ -814,6 +887,7 @@ void cs_b200_destroy(cs_b200_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->owns_matrix) { cudaFree(h->d_rowptr); cudaFree(h->d_colidx); cudaFree(h->d_vals); }
+  free_win(h->A0);
   for (size_t l = 0; l < h->lv.size(); ++l) {
     DevLevel& L = h->lv[l];
     if (l > 0) {

@@ -101,10 +101,12 @@ template <typename T> __device__ __forceinline__ void vstore(T* p, const T (&v)[
 // CTA (ticket) combines all CTAs in a fixed order into out[q*KT + c] (shared).
 // Returns true for every thread of the last CTA.
 // ---------------------------------------------------------------------------
-template <int KT, int VEC, int NV, bool IS_MAX>
+template <int KT, int VEC, int NV, bool IS_MAX, int NTH = NT>
 __device__ __forceinline__ bool grid_reduce(double (&val)[NV][VEC], double* partials,
                                             unsigned int* ticket, double* s_warp /*NWARP*NV*KT*/,
-                                            double* s_tree /*NT*/, double* out /*NV*KT*/) {
+                                            double* s_tree /*NTH*/, double* out /*NV*KT*/) {
+  constexpr int NWARP = NTH / 32;
+  constexpr int NT = NTH;
   constexpr int S = VEC < KT ? VEC : KT;  // distinct columns held per thread
   constexpr int G = KT / S;               // lane classes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -216,6 +218,10 @@ __device__ __forceinline__ void cg_after_precond(PanelCtl* ctl, const double* rh
 #define CSB_REDUCE_SMEM(NV, KT)                         \
   __shared__ double s_warp[NWARP * (NV) * (KT)];        \
   __shared__ double s_tree[NT];                         \
+  __shared__ double s_out[(NV) * (KT)];
+#define CSB_REDUCE_SMEM_W(NV, KT)                       \
+  __shared__ double s_warp[(WT / 32) * (NV) * (KT)];    \
+  __shared__ double s_tree[WT];                         \
   __shared__ double s_out[(NV) * (KT)];
 
 // ---------------------------------------------------------------------------
@@ -424,6 +430,265 @@ k_spmm(const CsrDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const Spmm
     double v[1][1] = {{dot0}};
     if (grid_reduce<KT, 1, 1, false>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out))
       cg_after_precond<KT>(ep.ctl, s_out);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// TMA-staged SpMM on the windowed row-block form (win_host.hpp).
+//
+// Persistent CTAs (one per SM, WT threads) walk the row blocks with a two-stage
+// shared-memory ring.  For block i+1 ONE elected thread arms an mbarrier with the
+// byte count and issues cp.async.bulk copies (the TMA engine; no registers, no LSU
+// instructions) of: the X-panel segments the block's columns fall into, the block's
+// B rows when the epilogue needs them, its slice of values, the 16-bit window-local
+// column indices and the row offsets -- while all WT threads compute block i out of
+// shared memory only.  Global memory sees nothing but large sequential bulk reads
+// and the coalesced Y stores.  Blocks flagged nseg == 0 (hub rows, scattered columns)
+// use direct gathers on the plain CSR inside the same kernel.
+// ---------------------------------------------------------------------------
+constexpr int WT = 512;                 // threads of the windowed kernel
+constexpr int W_RB = 256;               // must match csb_win::RB
+constexpr int W_WCAP = 1024;            // csb_win::WCAP
+constexpr int W_MAXSEG = 8;
+
+struct WinMeta {                        // == csb_win::BlockMeta
+  int row0, nrows, nnz, ent_off, roff_off, nseg, self_slot, wrows;
+  int seg_lo[W_MAXSEG];
+  int seg_len[W_MAXSEG];
+};
+
+template <typename T> struct WinCsr {
+  const WinMeta* meta;
+  const T* vals_p;
+  const unsigned short* lcol_p;
+  const unsigned short* roff_p;
+  // plain CSR for the direct-gather blocks
+  const int* rowptr;
+  const int* colidx;
+  const T* vals;
+  int nblocks;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+template <typename T, int KT, int MODE> struct WinSmem {
+  static constexpr bool NEEDB = (MODE == SP_RESNORM || MODE == SP_RES || MODE == SP_JACOBI ||
+                                 MODE == SP_JACOBI_DOT);
+  static constexpr int al(int x) { return (x + 127) / 128 * 128; }
+  static constexpr int XW = al(W_WCAP * KT * (int)sizeof(T));
+  static constexpr int BW = NEEDB ? al((W_RB + 8) * KT * (int)sizeof(T)) : 0;
+  static constexpr int VW = al(NNZ_CAP * (int)sizeof(T));
+  static constexpr int LW = al(NNZ_CAP * 2);
+  static constexpr int RW = al((W_RB + 8) * 2);
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_B = OFF_X + XW;
+  static constexpr int OFF_V = OFF_B + BW;
+  static constexpr int OFF_L = OFF_V + VW;
+  static constexpr int OFF_R = OFF_L + LW;
+  static constexpr int STAGE = OFF_R + RW;
+  static constexpr int TOTAL = 2 * STAGE;
+};
+
+template <typename T, int KT, int MODE, int LPR>
+__global__ void __launch_bounds__(WT, 1)
+k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
+  using SM = WinSmem<T, KT, MODE>;
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ unsigned long long full[2];
+  __shared__ double s_long[WT];
+  const int tid = threadIdx.x;
+  const int c = tid % KT;
+  const int lr = (tid / KT) % LPR;
+  constexpr int RPP = WT / (KT * LPR);
+  double dot0 = 0.0, dot1 = 0.0;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int blk, int st) {   // elected thread only
+    const WinMeta* m = A.meta + blk;
+    const int nseg = m->nseg;
+    if (nseg == 0) return;
+    unsigned char* base = dsm + st * SM::STAGE;
+    const int nnzp = (m->nnz + 7) / 8 * 8;
+    const int roffp = (m->nrows + 1 + 7) / 8 * 8;
+    const int b_lo = m->row0 & ~3;
+    const int b_len = ((m->row0 + m->nrows + 3) & ~3) - b_lo;
+    unsigned bytes = (unsigned)(m->wrows * KT * (int)sizeof(T) + nnzp * (int)sizeof(T) + nnzp * 2 + roffp * 2);
+    if (SM::NEEDB) bytes += (unsigned)(b_len * KT * (int)sizeof(T));
+    mbar_expect_tx(&full[st], bytes);
+    int slot = 0;
+    for (int k = 0; k < nseg; ++k) {
+      const int lo = m->seg_lo[k], len = m->seg_len[k];
+      bulk_g2s(base + SM::OFF_X + (size_t)slot * KT * sizeof(T), X + (size_t)lo * KT,
+               (unsigned)(len * KT * (int)sizeof(T)), &full[st]);
+      slot += len;
+    }
+    if (SM::NEEDB)
+      bulk_g2s(base + SM::OFF_B, ep.B + (size_t)b_lo * KT, (unsigned)(b_len * KT * (int)sizeof(T)), &full[st]);
+    bulk_g2s(base + SM::OFF_V, A.vals_p + m->ent_off, (unsigned)(nnzp * (int)sizeof(T)), &full[st]);
+    bulk_g2s(base + SM::OFF_L, A.lcol_p + m->ent_off, (unsigned)(nnzp * 2), &full[st]);
+    bulk_g2s(base + SM::OFF_R, A.roff_p + m->roff_off, (unsigned)(roffp * 2), &full[st]);
+  };
+
+  unsigned ph0 = 0, ph1 = 0;
+  int blk = blockIdx.x;
+  if (tid == 0 && blk < A.nblocks) issue(blk, 0);
+  for (int it = 0; blk < A.nblocks; blk += gridDim.x, ++it) {
+    const int st = it & 1;
+    const int nxt = blk + gridDim.x;
+    if (tid == 0 && nxt < A.nblocks) issue(nxt, st ^ 1);
+    const WinMeta* m = A.meta + blk;
+    const int row0 = m->row0, nr = m->nrows, nseg = m->nseg;
+    if (nseg > 0) {
+      const unsigned par = st ? ph1 : ph0;
+      while (!mbar_try_wait(&full[st], par)) {}
+      if (st) ph1 ^= 1u; else ph0 ^= 1u;
+      const unsigned char* base = dsm + st * SM::STAGE;
+      const T* xw = reinterpret_cast<const T*>(base + SM::OFF_X);
+      const T* bw = reinterpret_cast<const T*>(base + SM::OFF_B);
+      const T* vw = reinterpret_cast<const T*>(base + SM::OFF_V);
+      const unsigned short* lw = reinterpret_cast<const unsigned short*>(base + SM::OFF_L);
+      const unsigned short* rw = reinterpret_cast<const unsigned short*>(base + SM::OFF_R);
+      const int self = m->self_slot;
+      const int b_lo = row0 & ~3;
+      for (int basei = 0; basei < nr; basei += RPP) {
+        const int rl = basei + tid / (KT * LPR);
+        const bool valid = rl < nr;
+        T acc = T(0);
+        if (valid) {
+          const int a = rw[rl], b = rw[rl + 1];
+#pragma unroll 3
+          for (int j = a + lr; j < b; j += LPR) acc += vw[j] * xw[(int)lw[j] * KT + c];
+        }
+#pragma unroll
+        for (int off = KT; off < KT * LPR; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (valid && lr == 0) {
+          const int row = row0 + rl;
+          const size_t o = (size_t)row * KT + c;
+          // own-row X and B come from the staged copies when available
+          if (MODE == SP_PLAIN) {
+            Y[o] = acc;
+          } else if (MODE == SP_ADD) {
+            Y[o] += acc;
+          } else if (MODE == SP_CG) {
+            const T xo = self >= 0 ? xw[(self + rl) * KT + c] : X[o];
+            Y[o] = acc;
+            dot0 += (double)acc * (double)xo;
+          } else if (MODE == SP_RESNORM) {
+            const T bb = bw[(row - b_lo) * KT + c];
+            const T rr = bb - acc;
+            Y[o] = rr;
+            dot0 += (double)rr * (double)rr;
+            dot1 += (double)bb * (double)bb;
+          } else if (MODE == SP_RES) {
+            Y[o] = bw[(row - b_lo) * KT + c] - acc;
+          } else {
+            const T bb = bw[(row - b_lo) * KT + c];
+            const T xo = self >= 0 ? xw[(self + rl) * KT + c] : X[o];
+            const T yn = xo + ep.omega * ep.dinv[row] * (bb - acc);
+            Y[o] = yn;
+            if (MODE == SP_JACOBI_DOT) dot0 += (double)bb * (double)yn;
+          }
+        }
+      }
+    } else if (m->nnz <= NNZ_CAP && nr <= W_RB) {
+      // scattered block: direct gathers on the plain CSR
+      for (int basei = 0; basei < nr; basei += RPP) {
+        const int rl = basei + tid / (KT * LPR);
+        const bool valid = rl < nr;
+        const int row = row0 + rl;
+        T acc = T(0);
+        if (valid) {
+          const int a = A.rowptr[row], b = A.rowptr[row + 1];
+          for (int j = a + lr; j < b; j += LPR) acc += A.vals[j] * X[(size_t)A.colidx[j] * KT + c];
+        }
+#pragma unroll
+        for (int off = KT; off < KT * LPR; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (valid && lr == 0) spmm_epilogue<T, MODE>(row, (size_t)row * KT + c, acc, X, Y, ep, dot0, dot1);
+      }
+    } else {
+      // long row (its own block): the whole CTA strides over it
+      const int row = row0;
+      const int a = A.rowptr[row], b = A.rowptr[row + 1];
+      double acc = 0.0;
+      constexpr int GRP = WT / KT;
+      for (int j = a + tid / KT; j < b; j += GRP)
+        acc += (double)A.vals[j] * (double)X[(size_t)A.colidx[j] * KT + c];
+      s_long[tid] = acc;
+      __syncthreads();
+      if (tid < KT) {
+        double t = 0.0;
+        for (int g = 0; g < GRP; ++g) t += s_long[g * KT + tid];
+        spmm_epilogue<T, MODE>(row, (size_t)row * KT + tid, (T)t, X, Y, ep, dot0, dot1);
+      }
+    }
+    __syncthreads();   // stage `st` may be refilled from the next iteration on
+  }
+  if (MODE == SP_CG) {
+    CSB_REDUCE_SMEM_W(1, KT)
+    double v[1][1] = {{dot0}};
+    if (grid_reduce<KT, 1, 1, false, WT>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
+      if (tid < KT) {
+        const double pap = s_out[tid];
+        ep.ctl->pap[tid] = pap;
+        ep.ctl->alpha[tid] = (ep.ctl->active[tid] && pap > 0.0) ? ep.ctl->rho[tid] / pap : 0.0;
+      }
+    }
+  } else if (MODE == SP_RESNORM) {
+    CSB_REDUCE_SMEM_W(2, KT)
+    double v[2][1] = {{dot0}, {dot1}};
+    if (grid_reduce<KT, 1, 2, false, WT>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
+      if (tid < KT) {
+        ep.ctl->resid[tid] = s_out[tid];
+        ep.ctl->bnorm[tid] = s_out[KT + tid];
+      }
+    }
+  } else if (MODE == SP_JACOBI_DOT) {
+    CSB_REDUCE_SMEM_W(1, KT)
+    double v[1][1] = {{dot0}};
+    if (grid_reduce<KT, 1, 1, false, WT>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out))
+      cg_after_precond<KT>(ep.ctl, s_out);
+  }
+}
+
+// packed values of the windowed form:  vals_p[i] = perm[i] >= 0 ? vals[perm[i]] : 0
+template <typename T>
+__global__ void k_pack_vals(size_t n, const int* __restrict__ perm, const T* __restrict__ vals,
+                            T* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = perm[i];
+    out[i] = p >= 0 ? vals[p] : T(0);
   }
 }
 

@@ -39,6 +39,7 @@ class CUDASolver:
     panel_width: int = 8
     check_every: int = 16
     use_graph: bool = True
+    window: str = "auto"             # TMA-staged windowed SpMM: auto | on | off
 
     @property
     def dtype(self):
@@ -74,6 +75,7 @@ class B200Factor:
         opts.check_every = solver.check_every
         opts.use_graph = 1 if solver.use_graph else -1
         opts.log_transform = 1 if log_transform else 0
+        opts.window = {"auto": 0, "on": 1, "off": -1}[solver.window]
         rc = lib.cs_b200_create(self.n, m.nnz, _lib._ptr(rowptr), _lib._ptr(colidx), _lib._ptr(vals),
                                 bits, 0, _lib.dtype_code(self.dtype), solver.device,
                                 C.byref(opts), C.byref(self._h))

@@ -67,7 +67,9 @@ typedef struct cs_b200_opts {
                              Krylov.jl default in force at src/core.jl:639; <0 => none */
   double resid_gate;      /* true-residual gate (def 1e-4, src/core.jl:641)         */
   int32_t log_transform;  /* current maps accumulate log10(c) (src/out.jl:305-309)  */
-  int32_t reserved[7];
+  int32_t window;         /* TMA-staged windowed SpMM: 0 auto (operators >= 20000 rows),
+                             1 always, -1 never (plain direct-gather kernel)         */
+  int32_t reserved[6];
 } cs_b200_opts;
 
 /* Per-call statistics (milliseconds measured with CUDA events on the solve stream). */

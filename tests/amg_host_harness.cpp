@@ -31,3 +31,56 @@ void amgh_pinv(void* h, double* out) {
 }
 void amgh_free(void* h) { delete (Hierarchy*)h; }
 }
+
+// ---- windowed row-block form (win_host.hpp): host emulation of what k_spmm_win does ----
+#include "../circuitscape_b200/csrc/win_host.hpp"
+extern "C" long winh_spmv(long n, long nnz, const int* ptr, const int* idx, const double* val,
+                          const double* x, double* y, long* nblocks, long* max_wrows) {
+  // same greedy row blocks as cs_b200.cu:build_row_blocks
+  std::vector<int> bstart{0};
+  long r = 0;
+  while (r < n) {
+    long r1 = r + 1;
+    const long base = ptr[r];
+    while (r1 < n && (r1 - r) < csb_win::RB && (long)ptr[r1 + 1] - base <= csb_win::NNZ_CAP) ++r1;
+    bstart.push_back((int)r1);
+    r = r1;
+  }
+  const long n_pad = (n + 3) / 4 * 4;
+  std::vector<double> xp(n_pad, 0.0);
+  std::memcpy(xp.data(), x, n * sizeof(double));
+  csb_win::Windowed w = csb_win::build(ptr, idx, bstart, n_pad);
+  *nblocks = (long)w.meta.size();
+  *max_wrows = 0;
+  std::vector<double> win(csb_win::WCAP);
+  for (const auto& m : w.meta) {
+    if (m.nseg == 0) {
+      for (int row = m.row0; row < m.row0 + m.nrows; ++row) {
+        double s = 0;
+        for (int j = ptr[row]; j < ptr[row + 1]; ++j) s += val[j] * xp[idx[j]];
+        y[row] = s;
+      }
+      continue;
+    }
+    if (m.wrows > *max_wrows) *max_wrows = m.wrows;
+    int slot = 0;
+    for (int k = 0; k < m.nseg; ++k) {
+      if (m.seg_lo[k] % csb_win::ALN || m.seg_len[k] % csb_win::ALN || m.seg_lo[k] + m.seg_len[k] > n_pad) return -1;
+      for (int i = 0; i < m.seg_len[k]; ++i) win[slot + i] = xp[m.seg_lo[k] + i];
+      slot += m.seg_len[k];
+    }
+    if (slot != m.wrows || m.ent_off % 8 || m.roff_off % 8) return -2;
+    for (int rl = 0; rl < m.nrows; ++rl) {
+      const int a = w.roff[m.roff_off + rl], b = w.roff[m.roff_off + rl + 1];
+      double s = 0;
+      for (int j = a; j < b; ++j) {
+        const int p = w.perm_off[m.ent_off + j];
+        if (p < 0) return -3;
+        s += val[p] * win[w.lcol[m.ent_off + j]];
+      }
+      y[m.row0 + rl] = s;
+      if (m.self_slot >= 0 && win[m.self_slot + rl] != xp[m.row0 + rl]) return -4;
+    }
+  }
+  return w.windowed_blocks;
+}

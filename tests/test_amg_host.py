@@ -136,3 +136,39 @@ def test_spd_with_grounds_and_hub(harness):
     x, it = pcg(M, b, lambda r: vcycle(levels, pinv, r), rtol=1e-8)
     assert it <= 60, it
     assert np.linalg.norm(M @ x - b) / np.linalg.norm(b) < 1e-6
+
+
+def test_windowed_form_matches_csr(harness):
+    """win_host.hpp: the segment windows, 16-bit local columns, packed permutation and
+    row offsets reproduce y = A x exactly (host emulation of the TMA-staged kernel)."""
+    harness.winh_spmv.restype = C.c_long
+    harness.winh_spmv.argtypes = [C.c_long, C.c_long] + [C.c_void_p] * 7
+    rng = np.random.default_rng(0)
+    mats = []
+    A, _ = graph.synthetic_raster_laplacian(333, 217, seed=1)
+    mats.append(("raster", A, True))
+    g = 1.0 / np.exp(rng.normal(0, 1.0, (150, 140))); g[rng.random(g.shape) < 0.1] = 0
+    nm = graph.construct_node_map(g)
+    G = graph.laplacian(graph.construct_graph(g, nm, False, True))
+    mats.append(("holes4", G, True))
+    n = 6000
+    rows = np.repeat(np.arange(3, n), 3); cols = (rng.random(rows.size) ** 2 * rows).astype(np.int64)
+    rows = np.concatenate([rows, np.zeros(3000, dtype=np.int64)]); cols = np.concatenate([cols, np.arange(1, 3001)])
+    k = rows != cols
+    W = sp.coo_matrix((rng.random(k.sum()) + 0.1, (rows[k], cols[k])), shape=(n, n)).tocsr()
+    mats.append(("powerlaw", graph.laplacian(W + W.T), False))
+    for name, A, expect_win in mats:
+        A = sp.csr_matrix(A); A.sort_indices()
+        n = A.shape[0]
+        x = rng.standard_normal(n)
+        y = np.zeros(n)
+        ptr = A.indptr.astype(np.int32); idx = A.indices.astype(np.int32); val = A.data.astype(np.float64)
+        nb, mw = C.c_long(), C.c_long()
+        nwin = harness.winh_spmv(n, A.nnz, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data,
+                                 x.ctypes.data, y.ctypes.data, C.byref(nb), C.byref(mw))
+        assert nwin >= 0, (name, nwin)
+        ref = A @ x
+        assert np.abs(y - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), name
+        if expect_win:
+            assert nwin >= 0.95 * nb.value, (name, nwin, nb.value)
+            assert mw.value <= 1024
