@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -122,6 +123,17 @@ int set_err(cs_b200_handle* h, int code, const char* fmt, ...) {
                      cudaGetErrorString(_e), __FILE__, __LINE__, #call);                 \
   } while (0)
 
+// Host->device upload ordered on the handle's (non-blocking) stream.  NOT cudaMemcpy:
+// for pageable sources that call may return before the DMA of the last staged chunk has
+// landed and is only ordered against the legacy default stream -- a kernel on h->stream
+// launched right after could read a stale tail.
+cudaError_t h2d(cs_b200_handle* h, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(h->stream);   // the source buffers are short-lived host vectors
+}
+
 int kt_index(int kt) { return kt == 1 ? 0 : kt == 2 ? 1 : kt == 4 ? 2 : 3; }
 
 // greedy row blocks: <= NNZ_CAP nnz and <= NT rows; an over-long row stands alone.
@@ -143,6 +155,12 @@ int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* c
                    const std::vector<int>& bstart, int64_t ncols_pad);
 
 // upload one host CSR (double values) as a device CSR of T with its row blocks
+// debugging aid: CS_B200_WIN_MASK bit 0 = finest A, 1 = coarse A, 2 = P, 3 = R (default all)
+int win_mask() {
+  const char* e = getenv("CS_B200_WIN_MASK");
+  return e ? atoi(e) : 15;
+}
+
 template <typename T>
 int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowed) {
   d.nrows = (int)m.nrows;
@@ -156,11 +174,11 @@ int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowe
   CK(h, cudaMalloc(&d.colidx, std::max<size_t>(1, (size_t)d.nnz) * sizeof(int)));
   CK(h, cudaMalloc(&d.vals, std::max<size_t>(1, (size_t)d.nnz) * sizeof(T)));
   CK(h, cudaMalloc(&d.bstart, bstart.size() * sizeof(int)));
-  CK(h, cudaMemcpy(d.rowptr, m.ptr.data(), (size_t)(m.nrows + 1) * sizeof(int), cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(d.colidx, m.idx.data(), (size_t)d.nnz * sizeof(int), cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(d.vals, v.data(), (size_t)d.nnz * sizeof(T), cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(d.bstart, bstart.data(), bstart.size() * sizeof(int), cudaMemcpyHostToDevice));
-  if (h->opts.window >= 0 && (h->opts.window > 0 || windowed)) {
+  CK(h, h2d(h, d.rowptr, m.ptr.data(), (size_t)(m.nrows + 1) * sizeof(int)));
+  CK(h, h2d(h, d.colidx, m.idx.data(), (size_t)d.nnz * sizeof(int)));
+  CK(h, h2d(h, d.vals, v.data(), (size_t)d.nnz * sizeof(T)));
+  CK(h, h2d(h, d.bstart, bstart.data(), bstart.size() * sizeof(int)));
+  if (h->opts.window >= 0 && windowed) {
     const int64_t ncols_pad = (m.ncols + 3) / 4 * 4;
     return build_windowed<T>(h, d, m.ptr.data(), m.idx.data(), bstart, ncols_pad);
   }
@@ -194,10 +212,10 @@ int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* c
   CK(h, cudaMalloc(&d.lcol_p, ne * sizeof(unsigned short)));
   CK(h, cudaMalloc(&d.roff_p, w.roff.size() * sizeof(unsigned short)));
   CK(h, cudaMalloc(&d_perm, ne * sizeof(int)));
-  CK(h, cudaMemcpy(d.win_meta, w.meta.data(), w.meta.size() * sizeof(WinMeta), cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(d.lcol_p, w.lcol.data(), ne * sizeof(unsigned short), cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(d.roff_p, w.roff.data(), w.roff.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(d_perm, w.perm_off.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
+  CK(h, h2d(h, d.win_meta, w.meta.data(), w.meta.size() * sizeof(WinMeta)));
+  CK(h, h2d(h, d.lcol_p, w.lcol.data(), ne * sizeof(unsigned short)));
+  CK(h, h2d(h, d.roff_p, w.roff.data(), w.roff.size() * sizeof(unsigned short)));
+  CK(h, h2d(h, d_perm, w.perm_off.data(), ne * sizeof(int)));
   k_pack_vals<T><<<(int)std::min<size_t>(4096, (ne + 255) / 256), 256, 0, h->stream>>>(
       ne, d_perm, (const T*)d.vals, (T*)d.vals_p);
   CK(h, cudaGetLastError());
@@ -229,34 +247,34 @@ int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<i
       L.A = h->A0;  // alias, not owned
       L.dinv = h->d_dinv;
     } else {
-      int rc = upload_csr<T>(h, hl.A, L.A, L.n >= 20000);
+      int rc = upload_csr<T>(h, hl.A, L.A, L.n >= 20000 && (win_mask() & 2));
       if (rc) return rc;
       std::vector<T> dv(L.n_pad, T(0));
       for (int64_t i = 0; i < L.n; ++i) dv[i] = (T)hl.dinv[i];
       CK(h, cudaMalloc(&L.dinv, (size_t)L.n_pad * sizeof(T)));
-      CK(h, cudaMemcpy(L.dinv, dv.data(), (size_t)L.n_pad * sizeof(T), cudaMemcpyHostToDevice));
+      CK(h, h2d(h, L.dinv, dv.data(), (size_t)L.n_pad * sizeof(T)));
       const size_t pe = (size_t)L.n_pad * h->ktmax * sizeof(T);
       void** bufs[] = {&L.x, &L.b, &L.t, &L.y};
       for (void** bp : bufs) {
         CK(h, cudaMalloc(bp, pe));
-        CK(h, cudaMemset(*bp, 0, pe));
+        CK(h, cudaMemsetAsync(*bp, 0, pe, h->stream));
       }
     }
     if (l + 1 < nl) {
-      int rc = upload_csr<T>(h, hl.P, L.P, L.n >= 20000);
+      int rc = upload_csr<T>(h, hl.P, L.P, L.n >= 20000 && (win_mask() & 4));
       if (rc) return rc;
-      rc = upload_csr<T>(h, hl.R, L.R, L.n >= 20000);
+      rc = upload_csr<T>(h, hl.R, L.R, L.n >= 20000 && (win_mask() & 8));
       if (rc) return rc;
     }
   }
   const size_t nc = (size_t)hier.levels.back().A.nrows;
   if (hier.coarse_pinv.size() == nc * nc && nc > 0) {
     CK(h, cudaMalloc(&h->d_pinv, nc * nc * sizeof(double)));
-    CK(h, cudaMemcpy(h->d_pinv, hier.coarse_pinv.data(), nc * nc * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, h2d(h, h->d_pinv, hier.coarse_pinv.data(), nc * nc * sizeof(double)));
   }
   const size_t pe = (size_t)h->n_pad * h->ktmax * sizeof(T);
   CK(h, cudaMalloc(&h->Z, pe));
-  CK(h, cudaMemset(h->Z, 0, pe));
+  CK(h, cudaMemsetAsync(h->Z, 0, pe, h->stream));
   h->amg = nl > 1;
   return CS_B200_OK;
 }
@@ -291,7 +309,7 @@ int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std:
   CK(h, cudaStreamSynchronize(h->stream));
   std::vector<int> ci_local;
   std::vector<T> v_local;
-  const bool want_win = h->opts.window >= 0 && (h->opts.window > 0 || h->n >= 20000);
+  const bool want_win = h->opts.window >= 0 && (h->opts.window > 0 || h->n >= 20000) && (win_mask() & 1);
   const bool want_amg = h->opts.precond == CS_B200_PRECOND_AMG;
   if (!h_colidx && (want_win || want_amg)) {  // matrix arrived on the device (NCCL broadcast)
     ci_local.resize(h->nnz);
@@ -988,6 +1006,36 @@ int cs_b200_spmv(cs_b200_handle* h, const void* x, void* y, int reps, double* ms
   if (ms_per_rep) *ms_per_rep = ms / reps;
   h->stats.kernel_ms = ms;
   h->stats.h2d_bytes = h->stats.d2h_bytes = (double)bytes;
+  end_call(h);
+  return CS_B200_OK;
+}
+
+int cs_b200_spmm(cs_b200_handle* h, int k, const void* x, void* y) {
+  const bool add = getenv("CS_B200_SPMM_ADD") != nullptr;   // debug: Y = X + A X through SP_ADD
+  if (!h || !x || !y || (k != 1 && k != 2 && k != 4 && k != 8) || k > h->ktmax)
+    return set_err(h, CS_B200_ERR_ARG, "bad spmm arguments");
+  begin_call(h);
+  const size_t bytes = (size_t)h->n * k * h->esize();
+  const size_t nelem = (size_t)h->n_pad * k;
+  const int tg = (int)std::min<size_t>(4096, (nelem + 255) / 256);
+  CK(h, cudaMemcpyAsync(h->stage, x, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemsetAsync(h->X, 0, nelem * h->esize(), h->stream));
+  const bool f64 = h->dtype == CS_B200_F64;
+  if (f64) { DISPATCH_KT(k, (k_cm_to_panel<double, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const double*)h->stage, (double*)h->X, KT))); }
+  else { DISPATCH_KT(k, (k_cm_to_panel<float, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const float*)h->stage, (float*)h->X, KT))); }
+  if (add) {
+    CK(h, cudaMemcpyAsync(h->AP, h->X, nelem * h->esize(), cudaMemcpyDeviceToDevice, h->stream));
+    if (f64) { DISPATCH_KT(k, (launch_spmm<double, KT, SP_ADD>(h, (const double*)h->X, (double*)h->AP, nullptr))); }
+    else { DISPATCH_KT(k, (launch_spmm<float, KT, SP_ADD>(h, (const float*)h->X, (float*)h->AP, nullptr))); }
+  } else {
+  if (f64) { DISPATCH_KT(k, (launch_spmm<double, KT, SP_PLAIN>(h, (const double*)h->X, (double*)h->AP, nullptr))); }
+  else { DISPATCH_KT(k, (launch_spmm<float, KT, SP_PLAIN>(h, (const float*)h->X, (float*)h->AP, nullptr))); }
+  }
+  if (f64) { DISPATCH_KT(k, (k_panel_to_cm<double, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const double*)h->AP, (double*)h->stage, h->d_ctl, 0))); }
+  else { DISPATCH_KT(k, (k_panel_to_cm<float, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const float*)h->AP, (float*)h->stage, h->d_ctl, 0))); }
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(y, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
   end_call(h);
   return CS_B200_OK;
 }

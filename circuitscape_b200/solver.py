@@ -123,6 +123,14 @@ class B200Factor:
         _lib.check(self._lib, self._h, rc)
         return y, ms.value
 
+    def spmm(self, X):
+        """Y = A X for X (n, k), k in {1,2,4,8}, through the panel kernel."""
+        X = np.asfortranarray(X, dtype=self.dtype)
+        Y = np.empty_like(X, order="F")
+        rc = self._lib.cs_b200_spmm(self._h, X.shape[1], _lib._ptr(X), _lib._ptr(Y))
+        _lib.check(self._lib, self._h, rc)
+        return Y
+
     def bench_spmm(self, k, reps=20, flush_l2=False):
         ms = C.c_double()
         rc = self._lib.cs_b200_bench_spmm(self._h, k, reps, 1 if flush_l2 else 0, C.byref(ms))

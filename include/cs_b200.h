@@ -108,6 +108,10 @@ const char* cs_b200_last_error(const cs_b200_handle* h);
  * and parity hook for the headline kernel.                                          */
 int cs_b200_spmv(cs_b200_handle* h, const void* x, void* y, int reps, double* ms_per_rep);
 
+/* Y = A X for k in {1,2,4,8} columns through the panel SpMM kernel: x, y host,
+ * column-major n x k.  Parity hook for the batched kernel at any size.             */
+int cs_b200_spmm(cs_b200_handle* h, int k, const void* x, void* y);
+
 /* Y = A X for a row-major n x k panel resident on the device (k in 1,2,4,8),
  * timing only -- no host traffic.  flush_l2 != 0 writes a >L2 buffer between reps. */
 int cs_b200_bench_spmm(cs_b200_handle* h, int k, int reps, int flush_l2, double* ms_per_rep);

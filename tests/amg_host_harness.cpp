@@ -34,7 +34,13 @@ void amgh_free(void* h) { delete (Hierarchy*)h; }
 
 // ---- windowed row-block form (win_host.hpp): host emulation of what k_spmm_win does ----
 #include "../circuitscape_b200/csrc/win_host.hpp"
+extern "C" long winh_spmv_rect(long n, long ncols, long nnz, const int* ptr, const int* idx, const double* val,
+                          const double* x, double* y, long* nblocks, long* max_wrows);
 extern "C" long winh_spmv(long n, long nnz, const int* ptr, const int* idx, const double* val,
+                          const double* x, double* y, long* nblocks, long* max_wrows) {
+  return winh_spmv_rect(n, n, nnz, ptr, idx, val, x, y, nblocks, max_wrows);
+}
+extern "C" long winh_spmv_rect(long n, long ncols, long nnz, const int* ptr, const int* idx, const double* val,
                           const double* x, double* y, long* nblocks, long* max_wrows) {
   // same greedy row blocks as cs_b200.cu:build_row_blocks
   std::vector<int> bstart{0};
@@ -46,9 +52,9 @@ extern "C" long winh_spmv(long n, long nnz, const int* ptr, const int* idx, cons
     bstart.push_back((int)r1);
     r = r1;
   }
-  const long n_pad = (n + 3) / 4 * 4;
+  const long n_pad = (ncols + 3) / 4 * 4;
   std::vector<double> xp(n_pad, 0.0);
-  std::memcpy(xp.data(), x, n * sizeof(double));
+  std::memcpy(xp.data(), x, ncols * sizeof(double));
   csb_win::Windowed w = csb_win::build(ptr, idx, bstart, n_pad);
   *nblocks = (long)w.meta.size();
   *max_wrows = 0;
@@ -79,7 +85,7 @@ extern "C" long winh_spmv(long n, long nnz, const int* ptr, const int* idx, cons
         s += val[p] * win[w.lcol[m.ent_off + j]];
       }
       y[m.row0 + rl] = s;
-      if (m.self_slot >= 0 && win[m.self_slot + rl] != xp[m.row0 + rl]) return -4;
+      if (n == ncols && m.self_slot >= 0 && win[m.self_slot + rl] != xp[m.row0 + rl]) return -4;
     }
   }
   return w.windowed_blocks;
