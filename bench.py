@@ -306,14 +306,16 @@ def main():
 
     # ---- e2e: plug-in hook #2 with host RHS / solution buffers --------------------
     k = len(msrc)
-    rhs = np.zeros((n, k), dtype=factor.dtype, order="F")
+    tdt = torch.float64 if factor.dtype == np.float64 else torch.float32
+    # pinned host buffers, column-major n x k (a Julia Matrix): torch (k, n) row-major == (n, k) F-order
+    rhs = torch.zeros((k, n), dtype=tdt).pin_memory().numpy().T
+    lhs_buf = torch.zeros((k, n), dtype=tdt).pin_memory().numpy().T
     rhs[msrc, np.arange(k)] = -1.0
     rhs[mdst, np.arange(k)] = 1.0
 
     def step_e2e():
-        lhs = cb.solve_linear_system(factor, None, rhs)
-        lhs = lhs - lhs[msrc, np.arange(k)][None, :]            # src/core.jl:466-472
-        r = lhs[mdst, np.arange(k)]
+        lhs, _, _ = factor.solve_rhs(rhs, out=lhs_buf)          # hook #2 on pinned host buffers
+        r = lhs[mdst, np.arange(k)] - lhs[msrc, np.arange(k)]   # src/core.jl:466-472, 486-492
         if distributed:
             r = cdist.gather_pairs(mine, r, total_pairs, dist, device=dev)
         return r, factor.stats()
@@ -326,7 +328,7 @@ def main():
            "h2d_bytes_per_step": int(res_e[-1][1]["h2d_bytes"]) * world,
            "d2h_bytes_per_step": int(res_e[-1][1]["d2h_bytes"]) * world,
            "ms_per_step": wall_e * 1e3 / nst_e,
-           "through": "solve_linear_system(factor, matrix, rhs::Matrix) with host buffers"}
+           "through": "solve_linear_system(factor, matrix, rhs::Matrix) with pinned host n x k buffers"}
     assert np.abs(np.asarray(res_e[-1][0]) - np.asarray(R)).max() <= 1e-6 * np.abs(R).max()
 
     # ---- roofline of the dominant kernel: instrumented repeat of one timed step ---

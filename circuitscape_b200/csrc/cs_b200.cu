@@ -49,6 +49,7 @@ struct DevCsr {
   unsigned short* lcol_p = nullptr;
   unsigned short* roff_p = nullptr;
   int64_t win_blocks = 0;
+  int win_nblocks = 0;
 };
 
 // one multigrid level below the finest (the finest level aliases the handle's own CSR)
@@ -151,8 +152,7 @@ void build_row_blocks(const std::vector<int>& rowptr, int64_t n, std::vector<int
 }
 
 template <typename T>
-int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx,
-                   const std::vector<int>& bstart, int64_t ncols_pad);
+int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx, int64_t ncols_pad);
 
 // upload one host CSR (double values) as a device CSR of T with its row blocks
 // debugging aid: CS_B200_WIN_MASK bit 0 = finest A, 1 = coarse A, 2 = P, 3 = R (default all)
@@ -180,7 +180,7 @@ int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowe
   CK(h, h2d(h, d.bstart, bstart.data(), bstart.size() * sizeof(int)));
   if (h->opts.window >= 0 && windowed) {
     const int64_t ncols_pad = (m.ncols + 3) / 4 * 4;
-    return build_windowed<T>(h, d, m.ptr.data(), m.idx.data(), bstart, ncols_pad);
+    return build_windowed<T>(h, d, m.ptr.data(), m.idx.data(), ncols_pad);
   }
   return CS_B200_OK;
 }
@@ -199,12 +199,14 @@ void free_csr(DevCsr& d) {
 // Build + upload the windowed row-block form of a CSR already resident in `d`.
 // rowptr/colidx: host copies; ncols_pad: rows of the input panel (n_pad of the column space).
 template <typename T>
-int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx,
-                   const std::vector<int>& bstart, int64_t ncols_pad) {
+int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx, int64_t ncols_pad) {
   static_assert(sizeof(WinMeta) == sizeof(csb_win::BlockMeta), "meta layout");
-  csb_win::Windowed w = csb_win::build(rowptr, colidx, bstart, ncols_pad);
+  static_assert(W_RB == csb_win::RB && W_WCAP == csb_win::WCAP && W_NNZ == csb_win::NNZ_CAP &&
+                W_MAXSEG == csb_win::MAXSEG, "window geometry");
+  csb_win::Windowed w = csb_win::build(rowptr, colidx, d.nrows, ncols_pad);
   d.win_blocks = w.windowed_blocks;
-  if (w.windowed_blocks == 0) return CS_B200_OK;   // nothing gained: keep the plain kernel
+  d.win_nblocks = (int)w.meta.size();
+  if (w.windowed_blocks * 2 < (int64_t)w.meta.size()) return CS_B200_OK;   // mostly scattered: keep the plain kernel
   const size_t ne = w.lcol.size();
   int* d_perm = nullptr;
   CK(h, cudaMalloc(&d.win_meta, w.meta.size() * sizeof(WinMeta)));
@@ -322,7 +324,7 @@ int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std:
     }
   }
   if (want_win) {
-    int rc = build_windowed<T>(h, h->A0, h_rowptr.data(), h_colidx->data(), bstart, h->n_pad);
+    int rc = build_windowed<T>(h, h->A0, h_rowptr.data(), h_colidx->data(), h->n_pad);
     if (rc) return rc;
   }
   if (want_amg) {
@@ -400,8 +402,8 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
   const SpmmEpi<T> ep{B, dinv, (T)omega, h->d_ctl, h->d_partials};
   if (m.win_meta) {
     const WinCsr<T> w{m.win_meta, (const T*)m.vals_p, m.lcol_p, m.roff_p, m.rowptr, m.colidx,
-                      (const T*)m.vals, m.nblocks};
-    const int wg = std::max(1, std::min(h->num_sms, m.nblocks));
+                      (const T*)m.vals, m.win_nblocks};
+    const int wg = std::max(1, std::min(h->num_sms, m.win_nblocks));
     constexpr int SMEM = WinSmem<T, KT, MODE>::TOTAL;
     if (m.lpr == 4) {
       constexpr int L4 = (KT * 4 <= 32 ? 4 : 1);
@@ -409,9 +411,10 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
       if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, L4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
       k_spmm_win<T, KT, MODE, L4><<<wg, WT, SMEM, h->stream>>>(w, X, Y, ep);
     } else {
+      constexpr int L1 = KT >= 4 ? 1 : (KT == 2 ? 2 : 4);   // WT = 512 lanes over 128 rows x KT columns
       static bool once = false;
-      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
-      k_spmm_win<T, KT, MODE, 1><<<wg, WT, SMEM, h->stream>>>(w, X, Y, ep);
+      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
+      k_spmm_win<T, KT, MODE, L1><<<wg, WT, SMEM, h->stream>>>(w, X, Y, ep);
     }
   } else if (m.lpr == 4 && KT * 4 <= 32) {
     k_spmm<T, KT, MODE, (KT * 4 <= 32 ? 4 : 1)><<<grid, NT, 0, h->stream>>>(view<T>(m), X, Y, ep);

@@ -447,9 +447,11 @@ k_spmm(const CsrDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const Spmm
 // use direct gathers on the plain CSR inside the same kernel.
 // ---------------------------------------------------------------------------
 constexpr int WT = 512;                 // threads of the windowed kernel
-constexpr int W_RB = 256;               // must match csb_win::RB
-constexpr int W_WCAP = 1024;            // csb_win::WCAP
+constexpr int W_RB = 128;               // == csb_win::RB
+constexpr int W_NNZ = 1152;             // == csb_win::NNZ_CAP
+constexpr int W_WCAP = 512;             // == csb_win::WCAP
 constexpr int W_MAXSEG = 8;
+constexpr int W_SMEM_BUDGET = 208 * 1024;   // dynamic shared memory the ring may use
 
 struct WinMeta {                        // == csb_win::BlockMeta
   int row0, nrows, nnz, ent_off, roff_off, nseg, self_slot, wrows;
@@ -503,8 +505,8 @@ template <typename T, int KT, int MODE> struct WinSmem {
   static constexpr int al(int x) { return (x + 127) / 128 * 128; }
   static constexpr int XW = al(W_WCAP * KT * (int)sizeof(T));
   static constexpr int BW = NEEDB ? al((W_RB + 8) * KT * (int)sizeof(T)) : 0;
-  static constexpr int VW = al(NNZ_CAP * (int)sizeof(T));
-  static constexpr int LW = al(NNZ_CAP * 2);
+  static constexpr int VW = al(W_NNZ * (int)sizeof(T));
+  static constexpr int LW = al(W_NNZ * 2);
   static constexpr int RW = al((W_RB + 8) * 2);
   static constexpr int OFF_X = 0;
   static constexpr int OFF_B = OFF_X + XW;
@@ -512,7 +514,8 @@ template <typename T, int KT, int MODE> struct WinSmem {
   static constexpr int OFF_L = OFF_V + VW;
   static constexpr int OFF_R = OFF_L + LW;
   static constexpr int STAGE = OFF_R + RW;
-  static constexpr int TOTAL = 2 * STAGE;
+  static constexpr int NSTAGE = (W_SMEM_BUDGET / STAGE) >= 6 ? 6 : (W_SMEM_BUDGET / STAGE);   // >= 3 for every T, KT
+  static constexpr int TOTAL = NSTAGE * STAGE;
 };
 
 template <typename T, int KT, int MODE, int LPR>
@@ -520,7 +523,9 @@ __global__ void __launch_bounds__(WT, 1)
 k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
   using SM = WinSmem<T, KT, MODE>;
   extern __shared__ __align__(128) unsigned char dsm[];
-  __shared__ unsigned long long full[2];
+  constexpr int NS = SM::NSTAGE;
+  static_assert(NS >= 2, "ring needs two stages");
+  __shared__ unsigned long long full[NS];
   __shared__ double s_long[WT];
   const int tid = threadIdx.x;
   const int c = tid % KT;
@@ -529,8 +534,8 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
   double dot0 = 0.0, dot1 = 0.0;
 
   if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -561,19 +566,29 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
     bulk_g2s(base + SM::OFF_R, A.roff_p + m->roff_off, (unsigned)(roffp * 2), &full[st]);
   };
 
-  unsigned ph0 = 0, ph1 = 0;
+  // ring: NS-1 blocks are in flight ahead of the one being computed
+  unsigned phases = 0;   // bit s = parity to wait for on stage s
   int blk = blockIdx.x;
-  if (tid == 0 && blk < A.nblocks) issue(blk, 0);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NS - 1; ++i) {
+      const int b = blk + i * (int)gridDim.x;
+      if (b < A.nblocks) issue(b, i);
+    }
+  }
   for (int it = 0; blk < A.nblocks; blk += gridDim.x, ++it) {
-    const int st = it & 1;
-    const int nxt = blk + gridDim.x;
-    if (tid == 0 && nxt < A.nblocks) issue(nxt, st ^ 1);
+    const int st = it % NS;
+    {
+      // stage (it-1) % NS was released by the __syncthreads that ended the previous iteration
+      const int nxt = blk + (NS - 1) * (int)gridDim.x;
+      if (tid == 0 && nxt < A.nblocks) issue(nxt, (it + NS - 1) % NS);
+    }
     const WinMeta* m = A.meta + blk;
     const int row0 = m->row0, nr = m->nrows, nseg = m->nseg;
     if (nseg > 0) {
-      const unsigned par = st ? ph1 : ph0;
+      const unsigned par = (phases >> st) & 1u;
       while (!mbar_try_wait(&full[st], par)) {}
-      if (st) ph1 ^= 1u; else ph0 ^= 1u;
+      phases ^= 1u << st;
       const unsigned char* base = dsm + st * SM::STAGE;
       const T* xw = reinterpret_cast<const T*>(base + SM::OFF_X);
       const T* bw = reinterpret_cast<const T*>(base + SM::OFF_B);
@@ -622,7 +637,7 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
           }
         }
       }
-    } else if (m->nnz <= NNZ_CAP && nr <= W_RB) {
+    } else if (nr > 1 || m->nnz <= W_NNZ) {
       // scattered block: direct gathers on the plain CSR
       for (int basei = 0; basei < nr; basei += RPP) {
         const int rl = basei + tid / (KT * LPR);
@@ -653,7 +668,7 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
         spmm_epilogue<T, MODE>(row, (size_t)row * KT + tid, (T)t, X, Y, ep, dot0, dot1);
       }
     }
-    __syncthreads();   // stage `st` may be refilled from the next iteration on
+    __syncthreads();   // stage `st` is refilled at the start of the next iteration
   }
   if (MODE == SP_CG) {
     CSB_REDUCE_SMEM_W(1, KT)

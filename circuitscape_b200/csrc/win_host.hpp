@@ -1,9 +1,9 @@
 // win_host.hpp -- host-side construction of the "windowed row-block" form of a CSR
 // operator, the layout the TMA-staged SpMM kernel (k_spmm_win, kernels.cuh) consumes.
 //
-// For every row block (<= 256 consecutive rows, <= 2304 nnz) the set of columns it
+// For every row block (<= 128 consecutive rows, <= 1152 nnz) the set of columns it
 // touches is covered by a few contiguous *segments* of the X panel (for the raster
-// stencil with column-major numbering: three strips of ~258 rows).  The kernel bulk-
+// stencil with column-major numbering: three strips of ~130 rows).  The kernel bulk-
 // copies (cp.async.bulk + mbarrier) those segments, the block's slice of values, a
 // 16-bit *window-local* column index per entry and the block's row offsets into
 // shared memory, double-buffered across blocks, and then works out of shared memory
@@ -16,9 +16,9 @@
 
 namespace csb_win {
 
-constexpr int RB = 256;        // rows per block (== threads of the plain kernel)
-constexpr int NNZ_CAP = 2304;  // entries per block
-constexpr int WCAP = 1024;     // X rows staged per block (all segments together)
+constexpr int RB = 128;        // rows per block
+constexpr int NNZ_CAP = 1152;  // entries per block (128 rows x 9)
+constexpr int WCAP = 512;      // X rows staged per block (all segments together)
 constexpr int MAXSEG = 8;
 constexpr int ALN = 4;         // segment start/length granularity in X rows (16 B at KT=1, fp32)
 constexpr int MERGE_GAP = 16;  // runs closer than this are merged into one segment
@@ -43,10 +43,25 @@ struct Windowed {
   int64_t windowed_blocks = 0;
 };
 
-// bstart: row-block starts as used by the plain kernel (size nblocks+1)
-inline Windowed build(const int* rowptr, const int* colidx, const std::vector<int>& bstart,
+// greedy row blocks of the windowed form: <= RB rows and <= NNZ_CAP entries; a longer row
+// stands alone (and takes the direct-gather path)
+inline std::vector<int> row_blocks(const int* rowptr, int64_t n) {
+  std::vector<int> bstart{0};
+  int64_t r = 0;
+  while (r < n) {
+    int64_t r1 = r + 1;
+    const int64_t base = rowptr[r];
+    while (r1 < n && (r1 - r) < RB && (int64_t)rowptr[r1 + 1] - base <= NNZ_CAP) ++r1;
+    bstart.push_back((int)r1);
+    r = r1;
+  }
+  return bstart;
+}
+
+inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
                       int64_t ncols_pad /* X rows available (n_pad of the input panel) */) {
   Windowed w;
+  const std::vector<int> bstart = row_blocks(rowptr, nrows);
   const int nb = (int)bstart.size() - 1;
   w.meta.resize(nb);
   // pass 1: sizes

@@ -143,13 +143,15 @@ class B200Factor:
         _lib.check(self._lib, self._h, rc)
         return ms.value
 
-    def solve_rhs(self, rhs, rtol=None, itmax=None, raise_on_residual=True):
-        """rhs: (n,) or (n, k).  Returns (lhs, iters, relres)."""
+    def solve_rhs(self, rhs, rtol=None, itmax=None, raise_on_residual=True, out=None):
+        """rhs: (n,) or (n, k).  Returns (lhs, iters, relres).  `out`: optional
+        F-ordered (n, k) result buffer (e.g. pinned host memory)."""
         rhs = np.asarray(rhs, dtype=self.dtype)
         vec = rhs.ndim == 1
         b = np.asfortranarray(rhs.reshape(self.n, -1))
         k = b.shape[1]
-        x = np.empty_like(b, order="F")
+        x = out if out is not None else np.empty_like(b, order="F")
+        assert x.flags.f_contiguous and x.shape == b.shape and x.dtype == b.dtype
         iters = np.zeros(k, dtype=np.int64)
         relres = np.zeros(k, dtype=np.float64)
         rc = self._lib.cs_b200_solve_rhs(self._h, k, _lib._ptr(b), _lib._ptr(x),

@@ -42,20 +42,10 @@ extern "C" long winh_spmv(long n, long nnz, const int* ptr, const int* idx, cons
 }
 extern "C" long winh_spmv_rect(long n, long ncols, long nnz, const int* ptr, const int* idx, const double* val,
                           const double* x, double* y, long* nblocks, long* max_wrows) {
-  // same greedy row blocks as cs_b200.cu:build_row_blocks
-  std::vector<int> bstart{0};
-  long r = 0;
-  while (r < n) {
-    long r1 = r + 1;
-    const long base = ptr[r];
-    while (r1 < n && (r1 - r) < csb_win::RB && (long)ptr[r1 + 1] - base <= csb_win::NNZ_CAP) ++r1;
-    bstart.push_back((int)r1);
-    r = r1;
-  }
   const long n_pad = (ncols + 3) / 4 * 4;
   std::vector<double> xp(n_pad, 0.0);
   std::memcpy(xp.data(), x, ncols * sizeof(double));
-  csb_win::Windowed w = csb_win::build(ptr, idx, bstart, n_pad);
+  csb_win::Windowed w = csb_win::build(ptr, idx, n, n_pad);
   *nblocks = (long)w.meta.size();
   *max_wrows = 0;
   std::vector<double> win(csb_win::WCAP);

@@ -171,4 +171,4 @@ def test_windowed_form_matches_csr(harness):
         assert np.abs(y - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), name
         if expect_win:
             assert nwin >= 0.95 * nb.value, (name, nwin, nb.value)
-            assert mw.value <= 1024
+            assert mw.value <= 512
