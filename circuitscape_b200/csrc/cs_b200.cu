@@ -406,15 +406,15 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
     const int wg = std::max(1, std::min(h->num_sms, m.win_nblocks));
     constexpr int SMEM = WinSmem<T, KT, MODE>::TOTAL;
     if (m.lpr == 4) {
-      constexpr int L4 = (KT * 4 <= 32 ? 4 : 1);
+      constexpr int L4 = KT == 8 ? 8 : 16;   // wide rows (restrictions): more lanes per row
       static bool once = false;
       if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, L4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
-      k_spmm_win<T, KT, MODE, L4><<<wg, WT, SMEM, h->stream>>>(w, X, Y, ep);
+      k_spmm_win<T, KT, MODE, L4><<<wg, WTT, SMEM, h->stream>>>(w, X, Y, ep);
     } else {
-      constexpr int L1 = KT >= 4 ? 1 : (KT == 2 ? 2 : 4);   // WT = 512 lanes over 128 rows x KT columns
+      constexpr int L1 = KT == 8 ? 2 : 4;   // 512 consumer lanes over 128 rows x (KT/CPT) column groups
       static bool once = false;
       if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
-      k_spmm_win<T, KT, MODE, L1><<<wg, WT, SMEM, h->stream>>>(w, X, Y, ep);
+      k_spmm_win<T, KT, MODE, L1><<<wg, WTT, SMEM, h->stream>>>(w, X, Y, ep);
     }
   } else if (m.lpr == 4 && KT * 4 <= 32) {
     k_spmm<T, KT, MODE, (KT * 4 <= 32 ? 4 : 1)><<<grid, NT, 0, h->stream>>>(view<T>(m), X, Y, ep);

@@ -220,8 +220,8 @@ __device__ __forceinline__ void cg_after_precond(PanelCtl* ctl, const double* rh
   __shared__ double s_tree[NT];                         \
   __shared__ double s_out[(NV) * (KT)];
 #define CSB_REDUCE_SMEM_W(NV, KT)                       \
-  __shared__ double s_warp[(WT / 32) * (NV) * (KT)];    \
-  __shared__ double s_tree[WT];                         \
+  __shared__ double s_warp[(WTT / 32) * (NV) * (KT)];   \
+  __shared__ double s_tree[WTT];                        \
   __shared__ double s_out[(NV) * (KT)];
 
 // ---------------------------------------------------------------------------
@@ -446,7 +446,6 @@ k_spmm(const CsrDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const Spmm
 // and the coalesced Y stores.  Blocks flagged nseg == 0 (hub rows, scattered columns)
 // use direct gathers on the plain CSR inside the same kernel.
 // ---------------------------------------------------------------------------
-constexpr int WT = 512;                 // threads of the windowed kernel
 constexpr int W_RB = 128;               // == csb_win::RB
 constexpr int W_NNZ = 1152;             // == csb_win::NNZ_CAP
 constexpr int W_WCAP = 512;             // == csb_win::WCAP
@@ -518,162 +517,294 @@ template <typename T, int KT, int MODE> struct WinSmem {
   static constexpr int TOTAL = NSTAGE * STAGE;
 };
 
+// Warp-specialised: warps 0..15 (WC threads) consume, warp 16 produces.
+// The producer walks the CTA's contiguous range of row blocks: its lanes fetch the
+// block's 96-byte descriptor with ONE coalesced load, lane 0 posts a 16-byte header
+// (row0, nrows, nseg, self slot) into the stage and either arms full[stage] with the
+// byte count and issues the bulk copies, or (direct-gather block) just arrives.
+// Consumers wait full[stage], compute from shared memory, and each consumer warp
+// arrives on empty[stage]; the producer waits empty[stage] before refilling it.
+constexpr int WC = 512;                 // consumer threads
+constexpr int WTT = WC + 32;            // + producer warp
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() {   // named barrier 1: consumers only
+  asm volatile("bar.sync 1, %0;" ::"r"(WC) : "memory");
+}
+
+// N contiguous values through the widest aligned vector access (<= 16 B); p is aligned to
+// min(16, N*sizeof(T)) bytes by construction (rows of KT values, column groups of CPT).
+template <typename T, int N>
+__device__ __forceinline__ void ldvec(const T* p, T (&v)[N]) {
+  constexpr int BYTES = N * (int)sizeof(T);
+  if constexpr (BYTES >= 16) {
+    constexpr int PER = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int k = 0; k < N / PER; ++k) {
+      const uint4 t = *reinterpret_cast<const uint4*>(p + k * PER);
+      const T* q = reinterpret_cast<const T*>(&t);
+#pragma unroll
+      for (int i = 0; i < PER; ++i) v[k * PER + i] = q[i];
+    }
+  } else if constexpr (BYTES == 8) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const T* q = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = q[i];
+  } else {
+    v[0] = p[0];
+  }
+}
+template <typename T, int N>
+__device__ __forceinline__ void stvec(T* p, const T (&v)[N]) {
+  constexpr int BYTES = N * (int)sizeof(T);
+  if constexpr (BYTES >= 16) {
+    constexpr int PER = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int k = 0; k < N / PER; ++k) {
+      uint4 t;
+      T* q = reinterpret_cast<T*>(&t);
+#pragma unroll
+      for (int i = 0; i < PER; ++i) q[i] = v[k * PER + i];
+      *reinterpret_cast<uint4*>(p + k * PER) = t;
+    }
+  } else if constexpr (BYTES == 8) {
+    uint2 t;
+    T* q = reinterpret_cast<T*>(&t);
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = v[i];
+    *reinterpret_cast<uint2*>(p) = t;
+  } else {
+    p[0] = v[0];
+  }
+}
+
+template <typename T, int KT> struct WinMap {
+  static constexpr int CPT = KT >= 4 ? 4 : KT;      // panel columns per thread (vector LDS/STG)
+  static constexpr int CG = KT / CPT;               // column groups per row
+};
+
 template <typename T, int KT, int MODE, int LPR>
-__global__ void __launch_bounds__(WT, 1)
+__global__ void __launch_bounds__(WTT, 1)
 k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
   using SM = WinSmem<T, KT, MODE>;
-  extern __shared__ __align__(128) unsigned char dsm[];
+  using MP = WinMap<T, KT>;
   constexpr int NS = SM::NSTAGE;
+  constexpr int CPT = MP::CPT, CG = MP::CG;
   static_assert(NS >= 2, "ring needs two stages");
-  __shared__ unsigned long long full[NS];
-  __shared__ double s_long[WT];
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ unsigned long long full[NS], empty[NS];
+  __shared__ int4 hdr[NS];
+  __shared__ double s_long[WC];
   const int tid = threadIdx.x;
-  const int c = tid % KT;
-  const int lr = (tid / KT) % LPR;
-  constexpr int RPP = WT / (KT * LPR);
-  double dot0 = 0.0, dot1 = 0.0;
+  const bool producer = tid >= WC;
+  double dot0[CPT], dot1[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) dot0[i] = dot1[i] = 0.0;
 
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], WC / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  auto issue = [&](int blk, int st) {   // elected thread only
-    const WinMeta* m = A.meta + blk;
-    const int nseg = m->nseg;
-    if (nseg == 0) return;
-    unsigned char* base = dsm + st * SM::STAGE;
-    const int nnzp = (m->nnz + 7) / 8 * 8;
-    const int roffp = (m->nrows + 1 + 7) / 8 * 8;
-    const int b_lo = m->row0 & ~3;
-    const int b_len = ((m->row0 + m->nrows + 3) & ~3) - b_lo;
-    unsigned bytes = (unsigned)(m->wrows * KT * (int)sizeof(T) + nnzp * (int)sizeof(T) + nnzp * 2 + roffp * 2);
-    if (SM::NEEDB) bytes += (unsigned)(b_len * KT * (int)sizeof(T));
-    mbar_expect_tx(&full[st], bytes);
-    int slot = 0;
-    for (int k = 0; k < nseg; ++k) {
-      const int lo = m->seg_lo[k], len = m->seg_len[k];
-      bulk_g2s(base + SM::OFF_X + (size_t)slot * KT * sizeof(T), X + (size_t)lo * KT,
-               (unsigned)(len * KT * (int)sizeof(T)), &full[st]);
-      slot += len;
-    }
-    if (SM::NEEDB)
-      bulk_g2s(base + SM::OFF_B, ep.B + (size_t)b_lo * KT, (unsigned)(b_len * KT * (int)sizeof(T)), &full[st]);
-    bulk_g2s(base + SM::OFF_V, A.vals_p + m->ent_off, (unsigned)(nnzp * (int)sizeof(T)), &full[st]);
-    bulk_g2s(base + SM::OFF_L, A.lcol_p + m->ent_off, (unsigned)(nnzp * 2), &full[st]);
-    bulk_g2s(base + SM::OFF_R, A.roff_p + m->roff_off, (unsigned)(roffp * 2), &full[st]);
-  };
+  // contiguous range of row blocks per CTA
+  const int per = (A.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int b_begin = min((int)blockIdx.x * per, A.nblocks);
+  const int b_end = min(b_begin + per, A.nblocks);
 
-  // ring: NS-1 blocks are in flight ahead of the one being computed
-  unsigned phases = 0;   // bit s = parity to wait for on stage s
-  int blk = blockIdx.x;
-  if (tid == 0) {
+  if (producer) {
+    const int lane = tid & 31;
+    const int* mw = reinterpret_cast<const int*>(A.meta);
+    constexpr int MWORDS = (int)(sizeof(WinMeta) / 4);   // 24
+    int w_next = (b_begin < b_end && lane < MWORDS) ? mw[(size_t)b_begin * MWORDS + lane] : 0;
+    for (int blk = b_begin, it = 0; blk < b_end; ++blk, ++it) {
+      const int st = it % NS;
+      const int w = w_next;
+      if (blk + 1 < b_end && lane < MWORDS) w_next = mw[(size_t)(blk + 1) * MWORDS + lane];
+      if (it >= NS) {
+        const unsigned par = ((it / NS) - 1) & 1u;
+        while (!mbar_try_wait(&empty[st], par)) {}
+      }
+      // meta words: 0 row0, 1 nrows, 2 nnz, 3 ent_off, 4 roff_off, 5 nseg, 6 self_slot, 7 wrows, 8.. seg_lo, 16.. seg_len
+      const int row0 = __shfl_sync(0xffffffffu, w, 0), nrows = __shfl_sync(0xffffffffu, w, 1);
+      const int nnz = __shfl_sync(0xffffffffu, w, 2), ent_off = __shfl_sync(0xffffffffu, w, 3);
+      const int roff_off = __shfl_sync(0xffffffffu, w, 4), nseg = __shfl_sync(0xffffffffu, w, 5);
+      const int self = __shfl_sync(0xffffffffu, w, 6), wrows = __shfl_sync(0xffffffffu, w, 7);
+      const int my_lo = __shfl_sync(0xffffffffu, w, 8 + (lane & 7));
+      const int my_len = __shfl_sync(0xffffffffu, w, 16 + (lane & 7));
+      // exclusive prefix of segment lengths over lanes 0..7
+      int slot = (lane < nseg) ? my_len : 0;
 #pragma unroll
-    for (int i = 0; i < NS - 1; ++i) {
-      const int b = blk + i * (int)gridDim.x;
-      if (b < A.nblocks) issue(b, i);
-    }
-  }
-  for (int it = 0; blk < A.nblocks; blk += gridDim.x, ++it) {
-    const int st = it % NS;
-    {
-      // stage (it-1) % NS was released by the __syncthreads that ended the previous iteration
-      const int nxt = blk + (NS - 1) * (int)gridDim.x;
-      if (tid == 0 && nxt < A.nblocks) issue(nxt, (it + NS - 1) % NS);
-    }
-    const WinMeta* m = A.meta + blk;
-    const int row0 = m->row0, nr = m->nrows, nseg = m->nseg;
-    if (nseg > 0) {
-      const unsigned par = (phases >> st) & 1u;
-      while (!mbar_try_wait(&full[st], par)) {}
-      phases ^= 1u << st;
-      const unsigned char* base = dsm + st * SM::STAGE;
-      const T* xw = reinterpret_cast<const T*>(base + SM::OFF_X);
-      const T* bw = reinterpret_cast<const T*>(base + SM::OFF_B);
-      const T* vw = reinterpret_cast<const T*>(base + SM::OFF_V);
-      const unsigned short* lw = reinterpret_cast<const unsigned short*>(base + SM::OFF_L);
-      const unsigned short* rw = reinterpret_cast<const unsigned short*>(base + SM::OFF_R);
-      const int self = m->self_slot;
+      for (int off = 1; off < 8; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, slot, off);
+        if ((lane & 7) >= off) slot += v;
+      }
+      slot -= (lane < nseg) ? my_len : 0;
+      unsigned char* base = dsm + st * SM::STAGE;
+      if (lane == 0) hdr[st] = make_int4(row0, nrows, nseg, self);
+      if (nseg == 0) {
+        if (lane == 0) mbar_arrive(&full[st]);
+        continue;
+      }
+      const int nnzp = (nnz + 7) / 8 * 8;
+      const int roffp = (nrows + 1 + 7) / 8 * 8;
       const int b_lo = row0 & ~3;
-      for (int basei = 0; basei < nr; basei += RPP) {
-        const int rl = basei + tid / (KT * LPR);
-        const bool valid = rl < nr;
-        T acc = T(0);
-        if (valid) {
-          const int a = rw[rl], b = rw[rl + 1];
-#pragma unroll 3
-          for (int j = a + lr; j < b; j += LPR) acc += vw[j] * xw[(int)lw[j] * KT + c];
-        }
+      const int b_len = ((row0 + nrows + 3) & ~3) - b_lo;
+      if (lane == 0) {
+        unsigned bytes = (unsigned)(wrows * KT * (int)sizeof(T) + nnzp * (int)sizeof(T) + nnzp * 2 + roffp * 2);
+        if (SM::NEEDB) bytes += (unsigned)(b_len * KT * (int)sizeof(T));
+        mbar_expect_tx(&full[st], bytes);
+      }
+      __syncwarp();
+      // lanes 0..nseg-1: one X segment each; lanes 8..11: B, values, local columns, row offsets
+      if (lane < nseg)
+        bulk_g2s(base + SM::OFF_X + (size_t)slot * KT * sizeof(T), X + (size_t)my_lo * KT,
+                 (unsigned)(my_len * KT * (int)sizeof(T)), &full[st]);
+      if (SM::NEEDB && lane == 8)
+        bulk_g2s(base + SM::OFF_B, ep.B + (size_t)b_lo * KT, (unsigned)(b_len * KT * (int)sizeof(T)), &full[st]);
+      if (lane == 9) bulk_g2s(base + SM::OFF_V, A.vals_p + ent_off, (unsigned)(nnzp * (int)sizeof(T)), &full[st]);
+      if (lane == 10) bulk_g2s(base + SM::OFF_L, A.lcol_p + ent_off, (unsigned)(nnzp * 2), &full[st]);
+      if (lane == 11) bulk_g2s(base + SM::OFF_R, A.roff_p + roff_off, (unsigned)(roffp * 2), &full[st]);
+    }
+  } else {
+    const int cg = tid % CG;                       // column group of this thread
+    const int lr = (tid / CG) % LPR;               // lane within the row's entries
+    constexpr int LPRW = CG * LPR;                 // lanes per row
+    constexpr int RPP = WC / LPRW;                 // rows per pass
+    const int c0 = cg * CPT;
+    for (int blk = b_begin, it = 0; blk < b_end; ++blk, ++it) {
+      const int st = it % NS;
+      while (!mbar_try_wait(&full[st], (unsigned)((it / NS) & 1))) {}
+      const int4 h = hdr[st];
+      const int row0 = h.x, nr = h.y, nseg = h.z, self = h.w;
+      if (nseg > 0) {
+        const unsigned char* base = dsm + st * SM::STAGE;
+        const T* xw = reinterpret_cast<const T*>(base + SM::OFF_X);
+        const T* bw = reinterpret_cast<const T*>(base + SM::OFF_B);
+        const T* vw = reinterpret_cast<const T*>(base + SM::OFF_V);
+        const unsigned short* lw = reinterpret_cast<const unsigned short*>(base + SM::OFF_L);
+        const unsigned short* rw = reinterpret_cast<const unsigned short*>(base + SM::OFF_R);
+        const int b_lo = row0 & ~3;
+        for (int basei = 0; basei < nr; basei += RPP) {
+          const int rl = basei + tid / LPRW;
+          const bool valid = rl < nr;
+          T acc[CPT];
 #pragma unroll
-        for (int off = KT; off < KT * LPR; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (valid && lr == 0) {
-          const int row = row0 + rl;
-          const size_t o = (size_t)row * KT + c;
-          // own-row X and B come from the staged copies when available
-          if (MODE == SP_PLAIN) {
-            Y[o] = acc;
-          } else if (MODE == SP_ADD) {
-            Y[o] += acc;
-          } else if (MODE == SP_CG) {
-            const T xo = self >= 0 ? xw[(self + rl) * KT + c] : X[o];
-            Y[o] = acc;
-            dot0 += (double)acc * (double)xo;
-          } else if (MODE == SP_RESNORM) {
-            const T bb = bw[(row - b_lo) * KT + c];
-            const T rr = bb - acc;
-            Y[o] = rr;
-            dot0 += (double)rr * (double)rr;
-            dot1 += (double)bb * (double)bb;
-          } else if (MODE == SP_RES) {
-            Y[o] = bw[(row - b_lo) * KT + c] - acc;
-          } else {
-            const T bb = bw[(row - b_lo) * KT + c];
-            const T xo = self >= 0 ? xw[(self + rl) * KT + c] : X[o];
-            const T yn = xo + ep.omega * ep.dinv[row] * (bb - acc);
-            Y[o] = yn;
-            if (MODE == SP_JACOBI_DOT) dot0 += (double)bb * (double)yn;
+          for (int i = 0; i < CPT; ++i) acc[i] = T(0);
+          if (valid) {
+            const int a = rw[rl], b = rw[rl + 1];
+#pragma unroll 3
+            for (int j = a + lr; j < b; j += LPR) {
+              const T v = vw[j];
+              T xv[CPT];
+              ldvec<T, CPT>(xw + (int)lw[j] * KT + c0, xv);
+#pragma unroll
+              for (int i = 0; i < CPT; ++i) acc[i] += v * xv[i];
+            }
+          }
+#pragma unroll
+          for (int off = CG; off < LPRW; off <<= 1)
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+          if (valid && lr == 0) {
+            const int row = row0 + rl;
+            const size_t o = (size_t)row * KT + c0;
+            T out[CPT], bb[CPT], xo[CPT];
+            constexpr bool NEEDX = (MODE == SP_CG || MODE == SP_JACOBI || MODE == SP_JACOBI_DOT);
+            if (SM::NEEDB) ldvec<T, CPT>(bw + (row - b_lo) * KT + c0, bb);
+            if (NEEDX) {
+              if (self >= 0) ldvec<T, CPT>(xw + (self + rl) * KT + c0, xo);
+              else ldvec<T, CPT>(X + o, xo);
+            }
+            if (MODE == SP_ADD) ldvec<T, CPT>(Y + o, out);
+            T dv = T(0);
+            if (MODE == SP_JACOBI || MODE == SP_JACOBI_DOT) dv = ep.omega * ep.dinv[row];
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+              if (MODE == SP_PLAIN) {
+                out[i] = acc[i];
+              } else if (MODE == SP_ADD) {
+                out[i] += acc[i];
+              } else if (MODE == SP_CG) {
+                out[i] = acc[i];
+                dot0[i] += (double)acc[i] * (double)xo[i];
+              } else if (MODE == SP_RESNORM) {
+                const T rr = bb[i] - acc[i];
+                out[i] = rr;
+                dot0[i] += (double)rr * (double)rr;
+                dot1[i] += (double)bb[i] * (double)bb[i];
+              } else if (MODE == SP_RES) {
+                out[i] = bb[i] - acc[i];
+              } else {
+                const T yn = xo[i] + dv * (bb[i] - acc[i]);
+                out[i] = yn;
+                if (MODE == SP_JACOBI_DOT) dot0[i] += (double)bb[i] * (double)yn;
+              }
+            }
+            stvec<T, CPT>(Y + o, out);
           }
         }
-      }
-    } else if (nr > 1 || m->nnz <= W_NNZ) {
-      // scattered block: direct gathers on the plain CSR
-      for (int basei = 0; basei < nr; basei += RPP) {
-        const int rl = basei + tid / (KT * LPR);
-        const bool valid = rl < nr;
-        const int row = row0 + rl;
-        T acc = T(0);
-        if (valid) {
-          const int a = A.rowptr[row], b = A.rowptr[row + 1];
-          for (int j = a + lr; j < b; j += LPR) acc += A.vals[j] * X[(size_t)A.colidx[j] * KT + c];
-        }
+      } else if (nr > 1 || (A.rowptr[row0 + 1] - A.rowptr[row0]) <= W_NNZ) {
+        // scattered block: direct gathers on the plain CSR, same (row, column-group) ownership
+        for (int basei = 0; basei < nr; basei += WC / CG) {
+          const int rl = basei + tid / CG;
+          if (rl < nr) {
+            const int row = row0 + rl;
+            T acc[CPT];
 #pragma unroll
-        for (int off = KT; off < KT * LPR; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (valid && lr == 0) spmm_epilogue<T, MODE>(row, (size_t)row * KT + c, acc, X, Y, ep, dot0, dot1);
+            for (int i = 0; i < CPT; ++i) acc[i] = T(0);
+            for (int j = A.rowptr[row]; j < A.rowptr[row + 1]; ++j) {
+              const T v = A.vals[j];
+              const T* xp = X + (size_t)A.colidx[j] * KT + c0;
+#pragma unroll
+              for (int i = 0; i < CPT; ++i) acc[i] += v * xp[i];
+            }
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+              spmm_epilogue<T, MODE>(row, (size_t)row * KT + c0 + i, acc[i], X, Y, ep, dot0[i], dot1[i]);
+          }
+        }
+      } else {
+        // long row (its own block): all consumers stride over it; thread g < CG finalises
+        // its own CPT columns (same ownership as everywhere else)
+        const int row = row0;
+        const int c = tid % KT;
+        const int a = A.rowptr[row], b = A.rowptr[row + 1];
+        double acc = 0.0;
+        constexpr int GRP = WC / KT;
+        for (int j = a + tid / KT; j < b; j += GRP)
+          acc += (double)A.vals[j] * (double)X[(size_t)A.colidx[j] * KT + c];
+        consumer_sync();
+        s_long[tid] = acc;
+        consumer_sync();
+        if (tid < CG) {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            const int col = tid * CPT + i;
+            double t = 0.0;
+            for (int g = 0; g < GRP; ++g) t += s_long[g * KT + col];
+            spmm_epilogue<T, MODE>(row, (size_t)row * KT + col, (T)t, X, Y, ep, dot0[i], dot1[i]);
+          }
+        }
+        consumer_sync();
       }
-    } else {
-      // long row (its own block): the whole CTA strides over it
-      const int row = row0;
-      const int a = A.rowptr[row], b = A.rowptr[row + 1];
-      double acc = 0.0;
-      constexpr int GRP = WT / KT;
-      for (int j = a + tid / KT; j < b; j += GRP)
-        acc += (double)A.vals[j] * (double)X[(size_t)A.colidx[j] * KT + c];
-      s_long[tid] = acc;
-      __syncthreads();
-      if (tid < KT) {
-        double t = 0.0;
-        for (int g = 0; g < GRP; ++g) t += s_long[g * KT + tid];
-        spmm_epilogue<T, MODE>(row, (size_t)row * KT + tid, (T)t, X, Y, ep, dot0, dot1);
-      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[st]);
     }
-    __syncthreads();   // stage `st` is refilled at the start of the next iteration
   }
   if (MODE == SP_CG) {
     CSB_REDUCE_SMEM_W(1, KT)
-    double v[1][1] = {{dot0}};
-    if (grid_reduce<KT, 1, 1, false, WT>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
+    double v[1][CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) v[0][i] = dot0[i];
+    if (grid_reduce<KT, CPT, 1, false, WTT>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
       if (tid < KT) {
         const double pap = s_out[tid];
         ep.ctl->pap[tid] = pap;
@@ -682,8 +813,10 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
     }
   } else if (MODE == SP_RESNORM) {
     CSB_REDUCE_SMEM_W(2, KT)
-    double v[2][1] = {{dot0}, {dot1}};
-    if (grid_reduce<KT, 1, 2, false, WT>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
+    double v[2][CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { v[0][i] = dot0[i]; v[1][i] = dot1[i]; }
+    if (grid_reduce<KT, CPT, 2, false, WTT>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
       if (tid < KT) {
         ep.ctl->resid[tid] = s_out[tid];
         ep.ctl->bnorm[tid] = s_out[KT + tid];
@@ -691,8 +824,10 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
     }
   } else if (MODE == SP_JACOBI_DOT) {
     CSB_REDUCE_SMEM_W(1, KT)
-    double v[1][1] = {{dot0}};
-    if (grid_reduce<KT, 1, 1, false, WT>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out))
+    double v[1][CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) v[0][i] = dot0[i];
+    if (grid_reduce<KT, CPT, 1, false, WTT>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out))
       cg_after_precond<KT>(ep.ctl, s_out);
   }
 }
