@@ -403,18 +403,20 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
   if (m.win_meta) {
     const WinCsr<T> w{m.win_meta, (const T*)m.vals_p, m.lcol_p, m.roff_p, m.rowptr, m.colidx,
                       (const T*)m.vals, m.win_nblocks};
-    const int wg = std::max(1, std::min(h->num_sms, m.win_nblocks));
-    constexpr int SMEM = WinSmem<T, KT, MODE>::TOTAL;
     if (m.lpr == 4) {
-      constexpr int L4 = KT == 8 ? 8 : 16;   // wide rows (restrictions): more lanes per row
+      constexpr int SMEM = WinSmem2<T, KT, MODE, true>::TOTAL;
+      constexpr int SB = WinMap<T, KT, true>::SB;
+      const int wg = std::max(1, std::min(h->num_sms, (m.win_nblocks + SB - 1) / SB));
       static bool once = false;
-      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, L4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
-      k_spmm_win<T, KT, MODE, L4><<<wg, WTT, SMEM, h->stream>>>(w, X, Y, ep);
+      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
+      k_spmm_win<T, KT, MODE, true><<<wg, WTT, SMEM, h->stream>>>(w, X, Y, ep);
     } else {
-      constexpr int L1 = KT == 8 ? 2 : 4;   // 512 consumer lanes over 128 rows x (KT/CPT) column groups
+      constexpr int SMEM = WinSmem2<T, KT, MODE, false>::TOTAL;
+      constexpr int SB = WinMap<T, KT, false>::SB;
+      const int wg = std::max(1, std::min(h->num_sms, (m.win_nblocks + SB - 1) / SB));
       static bool once = false;
-      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
-      k_spmm_win<T, KT, MODE, L1><<<wg, WTT, SMEM, h->stream>>>(w, X, Y, ep);
+      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
+      k_spmm_win<T, KT, MODE, false><<<wg, WTT, SMEM, h->stream>>>(w, X, Y, ep);
     }
   } else if (m.lpr == 4 && KT * 4 <= 32) {
     k_spmm<T, KT, MODE, (KT * 4 <= 32 ? 4 : 1)><<<grid, NT, 0, h->stream>>>(view<T>(m), X, Y, ep);

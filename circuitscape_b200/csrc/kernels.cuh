@@ -450,7 +450,7 @@ constexpr int W_RB = 128;               // == csb_win::RB
 constexpr int W_NNZ = 1152;             // == csb_win::NNZ_CAP
 constexpr int W_WCAP = 512;             // == csb_win::WCAP
 constexpr int W_MAXSEG = 8;
-constexpr int W_SMEM_BUDGET = 208 * 1024;   // dynamic shared memory the ring may use
+constexpr int W_SMEM_BUDGET = 214 * 1024;   // dynamic shared memory the ring may use
 
 struct WinMeta {                        // == csb_win::BlockMeta
   int row0, nrows, nnz, ent_off, roff_off, nseg, self_slot, wrows;
@@ -581,22 +581,47 @@ __device__ __forceinline__ void stvec(T* p, const T (&v)[N]) {
   }
 }
 
-template <typename T, int KT> struct WinMap {
-  static constexpr int CPT = KT >= 4 ? 4 : KT;      // panel columns per thread (vector LDS/STG)
-  static constexpr int CG = KT / CPT;               // column groups per row
+// Work decomposition of the windowed kernel.  A ring stage holds SB consecutive row
+// blocks ("super-block"); consumer group g = tid / (WC/SB) owns sub-block g.  Within a
+// group a row is served by CG column groups (CPT = one 16-byte vector of the panel row
+// each -> conflict-free LDS.128 across the lanes of a row) times LPR lanes that split
+// the row's entries.  Sizes are chosen so that a full 128-row block occupies every
+// lane of its group once (narrow rows) and each lane has >= BATCH independent
+// load chains in flight.
+template <typename T, int KT, bool WIDE> struct WinMap {
+  static constexpr int V16 = 16 / (int)sizeof(T);
+  static constexpr int CPT = KT < V16 ? KT : V16;       // panel columns per thread
+  static constexpr int CG = KT / CPT;                   // column groups per row
+  static constexpr int SB = CG >= 4 ? 1 : (CG == 2 ? 1 : (KT == 1 ? 4 : 2));   // blocks per stage
+  static constexpr int GT = WC / SB;                    // threads per consumer group
+  static constexpr int LPR0 = (GT / W_RB) / CG < 1 ? 1 : (GT / W_RB) / CG;
+  static constexpr int LPR = WIDE ? (LPR0 * 4 * CG > 32 ? 32 / CG : LPR0 * 4) : LPR0;
+  static constexpr int LPRW = CG * LPR;                 // lanes per row
+  static constexpr int RPP = GT / LPRW;                 // rows per pass of a group
+  static constexpr int BATCH = WIDE ? 3 : (9 + LPR - 1) / LPR;   // entries per lane per batch
 };
 
-template <typename T, int KT, int MODE, int LPR>
+template <typename T, int KT, int MODE, bool WIDE> struct WinSmem2 {
+  using S1 = WinSmem<T, KT, MODE>;
+  static constexpr int SB = WinMap<T, KT, WIDE>::SB;
+  static constexpr int STAGE = S1::STAGE * SB;
+  static constexpr int NSTAGE = (W_SMEM_BUDGET / STAGE) >= 6 ? 6 : (W_SMEM_BUDGET / STAGE);
+  static constexpr int TOTAL = NSTAGE * STAGE;
+};
+
+template <typename T, int KT, int MODE, bool WIDE>
 __global__ void __launch_bounds__(WTT, 1)
 k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
   using SM = WinSmem<T, KT, MODE>;
-  using MP = WinMap<T, KT>;
-  constexpr int NS = SM::NSTAGE;
-  constexpr int CPT = MP::CPT, CG = MP::CG;
+  using S2 = WinSmem2<T, KT, MODE, WIDE>;
+  using MP = WinMap<T, KT, WIDE>;
+  constexpr int NS = S2::NSTAGE;
+  constexpr int SB = MP::SB, CPT = MP::CPT, CG = MP::CG, LPR = MP::LPR, LPRW = MP::LPRW;
+  constexpr int GT = MP::GT, RPP = MP::RPP, BATCH = MP::BATCH;
   static_assert(NS >= 2, "ring needs two stages");
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ unsigned long long full[NS], empty[NS];
-  __shared__ int4 hdr[NS];
+  __shared__ int4 hdr[NS][SB];
   __shared__ double s_long[WC];
   const int tid = threadIdx.x;
   const bool producer = tid >= WC;
@@ -607,85 +632,93 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], WC / 32);
+      mbar_init(&full[i], SB);          // one arrival per sub-block
+      mbar_init(&empty[i], WC / 32);    // one arrival per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // contiguous range of row blocks per CTA
-  const int per = (A.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int b_begin = min((int)blockIdx.x * per, A.nblocks);
-  const int b_end = min(b_begin + per, A.nblocks);
+  // super-blocks are dealt round-robin: at any time the CTAs work on a front of
+  // gridDim.x * SB consecutive row blocks, so the halo strips of X re-read by
+  // neighbouring blocks are still in L2.
+  const int nsuper = (A.nblocks + SB - 1) / SB;
 
   if (producer) {
     const int lane = tid & 31;
     const int* mw = reinterpret_cast<const int*>(A.meta);
     constexpr int MWORDS = (int)(sizeof(WinMeta) / 4);   // 24
-    int w_next = (b_begin < b_end && lane < MWORDS) ? mw[(size_t)b_begin * MWORDS + lane] : 0;
-    for (int blk = b_begin, it = 0; blk < b_end; ++blk, ++it) {
+    int it = 0;
+    for (int sbi = blockIdx.x; sbi < nsuper; sbi += gridDim.x, ++it) {
       const int st = it % NS;
-      const int w = w_next;
-      if (blk + 1 < b_end && lane < MWORDS) w_next = mw[(size_t)(blk + 1) * MWORDS + lane];
       if (it >= NS) {
         const unsigned par = ((it / NS) - 1) & 1u;
         while (!mbar_try_wait(&empty[st], par)) {}
       }
-      // meta words: 0 row0, 1 nrows, 2 nnz, 3 ent_off, 4 roff_off, 5 nseg, 6 self_slot, 7 wrows, 8.. seg_lo, 16.. seg_len
-      const int row0 = __shfl_sync(0xffffffffu, w, 0), nrows = __shfl_sync(0xffffffffu, w, 1);
-      const int nnz = __shfl_sync(0xffffffffu, w, 2), ent_off = __shfl_sync(0xffffffffu, w, 3);
-      const int roff_off = __shfl_sync(0xffffffffu, w, 4), nseg = __shfl_sync(0xffffffffu, w, 5);
-      const int self = __shfl_sync(0xffffffffu, w, 6), wrows = __shfl_sync(0xffffffffu, w, 7);
-      const int my_lo = __shfl_sync(0xffffffffu, w, 8 + (lane & 7));
-      const int my_len = __shfl_sync(0xffffffffu, w, 16 + (lane & 7));
-      // exclusive prefix of segment lengths over lanes 0..7
-      int slot = (lane < nseg) ? my_len : 0;
+#pragma unroll 1
+      for (int g = 0; g < SB; ++g) {
+        const int blk = sbi * SB + g;
+        if (blk >= A.nblocks) {               // tail of the last super-block
+          if (lane == 0) { hdr[st][g] = make_int4(0, 0, 0, -1); mbar_arrive(&full[st]); }
+          continue;
+        }
+        const int w = lane < MWORDS ? mw[(size_t)blk * MWORDS + lane] : 0;
+        // meta words: 0 row0, 1 nrows, 2 nnz, 3 ent_off, 4 roff_off, 5 nseg, 6 self_slot, 7 wrows,
+        //             8.. seg_lo, 16.. seg_len
+        const int row0 = __shfl_sync(0xffffffffu, w, 0), nrows = __shfl_sync(0xffffffffu, w, 1);
+        const int nnz = __shfl_sync(0xffffffffu, w, 2), ent_off = __shfl_sync(0xffffffffu, w, 3);
+        const int roff_off = __shfl_sync(0xffffffffu, w, 4), nseg = __shfl_sync(0xffffffffu, w, 5);
+        const int self = __shfl_sync(0xffffffffu, w, 6), wrows = __shfl_sync(0xffffffffu, w, 7);
+        const int my_lo = __shfl_sync(0xffffffffu, w, 8 + (lane & 7));
+        const int my_len = __shfl_sync(0xffffffffu, w, 16 + (lane & 7));
+        int slot = (lane < nseg) ? my_len : 0;    // exclusive prefix of segment lengths
 #pragma unroll
-      for (int off = 1; off < 8; off <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, slot, off);
-        if ((lane & 7) >= off) slot += v;
+        for (int off = 1; off < 8; off <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, slot, off);
+          if ((lane & 7) >= off) slot += v;
+        }
+        slot -= (lane < nseg) ? my_len : 0;
+        unsigned char* base = dsm + st * S2::STAGE + g * SM::STAGE;
+        if (lane == 0) hdr[st][g] = make_int4(row0, nrows, nseg, self);
+        if (nseg == 0) {
+          if (lane == 0) mbar_arrive(&full[st]);
+          continue;
+        }
+        const int nnzp = (nnz + 7) / 8 * 8;
+        const int roffp = (nrows + 1 + 7) / 8 * 8;
+        const int b_lo = row0 & ~3;
+        const int b_len = ((row0 + nrows + 3) & ~3) - b_lo;
+        if (lane == 0) {
+          unsigned bytes = (unsigned)(wrows * KT * (int)sizeof(T) + nnzp * (int)sizeof(T) + nnzp * 2 + roffp * 2);
+          if (SM::NEEDB) bytes += (unsigned)(b_len * KT * (int)sizeof(T));
+          mbar_expect_tx(&full[st], bytes);
+        }
+        __syncwarp();
+        // lanes 0..nseg-1: one X segment each; lanes 8..11: B, values, local columns, row offsets
+        if (lane < nseg)
+          bulk_g2s(base + SM::OFF_X + (size_t)slot * KT * sizeof(T), X + (size_t)my_lo * KT,
+                   (unsigned)(my_len * KT * (int)sizeof(T)), &full[st]);
+        if (SM::NEEDB && lane == 8)
+          bulk_g2s(base + SM::OFF_B, ep.B + (size_t)b_lo * KT, (unsigned)(b_len * KT * (int)sizeof(T)), &full[st]);
+        if (lane == 9) bulk_g2s(base + SM::OFF_V, A.vals_p + ent_off, (unsigned)(nnzp * (int)sizeof(T)), &full[st]);
+        if (lane == 10) bulk_g2s(base + SM::OFF_L, A.lcol_p + ent_off, (unsigned)(nnzp * 2), &full[st]);
+        if (lane == 11) bulk_g2s(base + SM::OFF_R, A.roff_p + roff_off, (unsigned)(roffp * 2), &full[st]);
       }
-      slot -= (lane < nseg) ? my_len : 0;
-      unsigned char* base = dsm + st * SM::STAGE;
-      if (lane == 0) hdr[st] = make_int4(row0, nrows, nseg, self);
-      if (nseg == 0) {
-        if (lane == 0) mbar_arrive(&full[st]);
-        continue;
-      }
-      const int nnzp = (nnz + 7) / 8 * 8;
-      const int roffp = (nrows + 1 + 7) / 8 * 8;
-      const int b_lo = row0 & ~3;
-      const int b_len = ((row0 + nrows + 3) & ~3) - b_lo;
-      if (lane == 0) {
-        unsigned bytes = (unsigned)(wrows * KT * (int)sizeof(T) + nnzp * (int)sizeof(T) + nnzp * 2 + roffp * 2);
-        if (SM::NEEDB) bytes += (unsigned)(b_len * KT * (int)sizeof(T));
-        mbar_expect_tx(&full[st], bytes);
-      }
-      __syncwarp();
-      // lanes 0..nseg-1: one X segment each; lanes 8..11: B, values, local columns, row offsets
-      if (lane < nseg)
-        bulk_g2s(base + SM::OFF_X + (size_t)slot * KT * sizeof(T), X + (size_t)my_lo * KT,
-                 (unsigned)(my_len * KT * (int)sizeof(T)), &full[st]);
-      if (SM::NEEDB && lane == 8)
-        bulk_g2s(base + SM::OFF_B, ep.B + (size_t)b_lo * KT, (unsigned)(b_len * KT * (int)sizeof(T)), &full[st]);
-      if (lane == 9) bulk_g2s(base + SM::OFF_V, A.vals_p + ent_off, (unsigned)(nnzp * (int)sizeof(T)), &full[st]);
-      if (lane == 10) bulk_g2s(base + SM::OFF_L, A.lcol_p + ent_off, (unsigned)(nnzp * 2), &full[st]);
-      if (lane == 11) bulk_g2s(base + SM::OFF_R, A.roff_p + roff_off, (unsigned)(roffp * 2), &full[st]);
     }
   } else {
-    const int cg = tid % CG;                       // column group of this thread
-    const int lr = (tid / CG) % LPR;               // lane within the row's entries
-    constexpr int LPRW = CG * LPR;                 // lanes per row
-    constexpr int RPP = WC / LPRW;                 // rows per pass
+    const int g = tid / GT;                        // consumer group = sub-block
+    const int gt = tid % GT;                       // thread within the group
+    const int cg = gt % CG;                        // column group of this thread
+    const int lr = (gt / CG) % LPR;                // lane within the row's entries
     const int c0 = cg * CPT;
-    for (int blk = b_begin, it = 0; blk < b_end; ++blk, ++it) {
+    int it = 0;
+    for (int sbi = blockIdx.x; sbi < nsuper; sbi += gridDim.x, ++it) {
       const int st = it % NS;
       while (!mbar_try_wait(&full[st], (unsigned)((it / NS) & 1))) {}
-      const int4 h = hdr[st];
+      const int4 h = hdr[st][g];
       const int row0 = h.x, nr = h.y, nseg = h.z, self = h.w;
       if (nseg > 0) {
-        const unsigned char* base = dsm + st * SM::STAGE;
+        const unsigned char* base = dsm + st * S2::STAGE + g * SM::STAGE;
         const T* xw = reinterpret_cast<const T*>(base + SM::OFF_X);
         const T* bw = reinterpret_cast<const T*>(base + SM::OFF_B);
         const T* vw = reinterpret_cast<const T*>(base + SM::OFF_V);
@@ -693,20 +726,31 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
         const unsigned short* rw = reinterpret_cast<const unsigned short*>(base + SM::OFF_R);
         const int b_lo = row0 & ~3;
         for (int basei = 0; basei < nr; basei += RPP) {
-          const int rl = basei + tid / LPRW;
+          const int rl = basei + gt / LPRW;
           const bool valid = rl < nr;
           T acc[CPT];
 #pragma unroll
           for (int i = 0; i < CPT; ++i) acc[i] = T(0);
           if (valid) {
             const int a = rw[rl], b = rw[rl + 1];
-#pragma unroll 3
-            for (int j = a + lr; j < b; j += LPR) {
-              const T v = vw[j];
-              T xv[CPT];
-              ldvec<T, CPT>(xw + (int)lw[j] * KT + c0, xv);
+            for (int j0 = a + lr; j0 < b; j0 += LPR * BATCH) {
+              // BATCH independent chains: values + local columns, then the X vectors, then FMAs
+              T v[BATCH];
+              int sl[BATCH];
 #pragma unroll
-              for (int i = 0; i < CPT; ++i) acc[i] += v * xv[i];
+              for (int u = 0; u < BATCH; ++u) {
+                const int j = j0 + u * LPR;
+                const bool ok = j < b;
+                v[u] = ok ? vw[j] : T(0);
+                sl[u] = ok ? (int)lw[j] : 0;
+              }
+              T xv[BATCH][CPT];
+#pragma unroll
+              for (int u = 0; u < BATCH; ++u) ldvec<T, CPT>(xw + sl[u] * KT + c0, xv[u]);
+#pragma unroll
+              for (int u = 0; u < BATCH; ++u)
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) acc[i] += v[u] * xv[u][i];
             }
           }
 #pragma unroll
@@ -751,10 +795,10 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
             stvec<T, CPT>(Y + o, out);
           }
         }
-      } else if (nr > 1 || (A.rowptr[row0 + 1] - A.rowptr[row0]) <= W_NNZ) {
+      } else if (nr > 1 || (nr == 1 && (A.rowptr[row0 + 1] - A.rowptr[row0]) <= W_NNZ)) {
         // scattered block: direct gathers on the plain CSR, same (row, column-group) ownership
-        for (int basei = 0; basei < nr; basei += WC / CG) {
-          const int rl = basei + tid / CG;
+        for (int basei = 0; basei < nr; basei += GT / CG) {
+          const int rl = basei + gt / CG;
           if (rl < nr) {
             const int row = row0 + rl;
             T acc[CPT];
@@ -762,35 +806,47 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
             for (int i = 0; i < CPT; ++i) acc[i] = T(0);
             for (int j = A.rowptr[row]; j < A.rowptr[row + 1]; ++j) {
               const T v = A.vals[j];
-              const T* xp = X + (size_t)A.colidx[j] * KT + c0;
+              T xv[CPT];
+              ldvec<T, CPT>(X + (size_t)A.colidx[j] * KT + c0, xv);
 #pragma unroll
-              for (int i = 0; i < CPT; ++i) acc[i] += v * xp[i];
+              for (int i = 0; i < CPT; ++i) acc[i] += v * xv[i];
             }
 #pragma unroll
             for (int i = 0; i < CPT; ++i)
               spmm_epilogue<T, MODE>(row, (size_t)row * KT + c0 + i, acc[i], X, Y, ep, dot0[i], dot1[i]);
           }
         }
-      } else {
-        // long row (its own block): all consumers stride over it; thread g < CG finalises
-        // its own CPT columns (same ownership as everywhere else)
+      } else if (nr == 1) {
+        // long row (its own block): the group's GT threads stride over it; thread q < CG of the
+        // group finalises its own CPT columns (same ownership as everywhere else)
         const int row = row0;
-        const int c = tid % KT;
+        const int c = gt % KT;
         const int a = A.rowptr[row], b = A.rowptr[row + 1];
         double acc = 0.0;
-        constexpr int GRP = WC / KT;
-        for (int j = a + tid / KT; j < b; j += GRP)
+        constexpr int GRP = GT / KT;
+        for (int j = a + gt / KT; j < b; j += GRP)
           acc += (double)A.vals[j] * (double)X[(size_t)A.colidx[j] * KT + c];
-        consumer_sync();
         s_long[tid] = acc;
+      }
+      // long rows need a group-wide exchange; every consumer takes the same barrier sequence
+      // (sub-blocks of one stage may differ, so the test is on "any long row in this stage")
+      bool any_long = false;
+#pragma unroll
+      for (int q = 0; q < SB; ++q) {
+        const int4 hq = hdr[st][q];
+        any_long |= (hq.z == 0 && hq.y == 1 && (A.rowptr[hq.x + 1] - A.rowptr[hq.x]) > W_NNZ);
+      }
+      if (any_long) {
         consumer_sync();
-        if (tid < CG) {
+        const bool mine = nseg == 0 && nr == 1 && (A.rowptr[row0 + 1] - A.rowptr[row0]) > W_NNZ;
+        if (mine && gt < CG) {
+          constexpr int GRP = GT / KT;
 #pragma unroll
           for (int i = 0; i < CPT; ++i) {
-            const int col = tid * CPT + i;
+            const int col = gt * CPT + i;
             double t = 0.0;
-            for (int g = 0; g < GRP; ++g) t += s_long[g * KT + col];
-            spmm_epilogue<T, MODE>(row, (size_t)row * KT + col, (T)t, X, Y, ep, dot0[i], dot1[i]);
+            for (int q = 0; q < GRP; ++q) t += s_long[g * GT + q * KT + col];
+            spmm_epilogue<T, MODE>(row0, (size_t)row0 * KT + col, (T)t, X, Y, ep, dot0[i], dot1[i]);
           }
         }
         consumer_sync();
