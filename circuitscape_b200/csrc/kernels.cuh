@@ -648,21 +648,39 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
     const int lane = tid & 31;
     const int* mw = reinterpret_cast<const int*>(A.meta);
     constexpr int MWORDS = (int)(sizeof(WinMeta) / 4);   // 24
-    int it = 0;
-    for (int sbi = blockIdx.x; sbi < nsuper; sbi += gridDim.x, ++it) {
-      const int st = it % NS;
-      if (it >= NS) {
-        const unsigned par = ((it / NS) - 1) & 1u;
-        while (!mbar_try_wait(&empty[st], par)) {}
-      }
-#pragma unroll 1
-      for (int g = 0; g < SB; ++g) {
-        const int blk = sbi * SB + g;
+    // Descriptor prefetch: slots q = 0,1,2,... enumerate (stage iteration, sub-block) pairs of
+    // this CTA; the 96-byte descriptors of the next PD slots are already in flight (one
+    // coalesced load each) while the current PD slots are being issued.
+    constexpr int PD = 4;
+    const int nmine = nsuper > (int)blockIdx.x ? (nsuper - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nslots = nmine * SB;
+    auto slot_block = [&](int q) { return ((int)blockIdx.x + (q / SB) * (int)gridDim.x) * SB + (q % SB); };
+    auto fetch = [&](int q) {
+      const int blk = q < nslots ? slot_block(q) : A.nblocks;
+      return (blk < A.nblocks && lane < MWORDS) ? mw[(size_t)blk * MWORDS + lane] : 0;
+    };
+    int wcur[PD], wnxt[PD];
+#pragma unroll
+    for (int u = 0; u < PD; ++u) wcur[u] = fetch(u);
+    for (int q0 = 0; q0 < nslots; q0 += PD) {
+#pragma unroll
+      for (int u = 0; u < PD; ++u) wnxt[u] = fetch(q0 + PD + u);
+#pragma unroll
+      for (int u = 0; u < PD; ++u) {
+        const int q = q0 + u;
+        if (q >= nslots) break;
+        const int it = q / SB, g = q % SB;
+        const int st = it % NS;
+        const int blk = slot_block(q);
+        if (g == 0 && it >= NS) {
+          const unsigned par = ((it / NS) - 1) & 1u;
+          while (!mbar_try_wait(&empty[st], par)) {}
+        }
         if (blk >= A.nblocks) {               // tail of the last super-block
           if (lane == 0) { hdr[st][g] = make_int4(0, 0, 0, -1); mbar_arrive(&full[st]); }
           continue;
         }
-        const int w = lane < MWORDS ? mw[(size_t)blk * MWORDS + lane] : 0;
+        const int w = wcur[u];
         // meta words: 0 row0, 1 nrows, 2 nnz, 3 ent_off, 4 roff_off, 5 nseg, 6 self_slot, 7 wrows,
         //             8.. seg_lo, 16.. seg_len
         const int row0 = __shfl_sync(0xffffffffu, w, 0), nrows = __shfl_sync(0xffffffffu, w, 1);
@@ -704,6 +722,8 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
         if (lane == 10) bulk_g2s(base + SM::OFF_L, A.lcol_p + ent_off, (unsigned)(nnzp * 2), &full[st]);
         if (lane == 11) bulk_g2s(base + SM::OFF_R, A.roff_p + roff_off, (unsigned)(roffp * 2), &full[st]);
       }
+#pragma unroll
+      for (int u = 0; u < PD; ++u) wcur[u] = wnxt[u];
     }
   } else {
     const int g = tid / GT;                        // consumer group = sub-block
