@@ -45,9 +45,7 @@ struct DevCsr {
   int lpr = 1;  // lanes per row used by k_spmm for this matrix
   // windowed row-block form for the TMA-staged kernel (win_host.hpp); null => plain kernel
   WinMeta* win_meta = nullptr;
-  void* vals_p = nullptr;
-  unsigned short* lcol_p = nullptr;
-  unsigned short* roff_p = nullptr;
+  unsigned char* blob = nullptr;   // per-block records [values | local columns | row offsets]
   int64_t win_blocks = 0;
   int win_nblocks = 0;
 };
@@ -186,8 +184,8 @@ int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowe
 }
 
 void free_win(DevCsr& d) {
-  cudaFree(d.win_meta); cudaFree(d.vals_p); cudaFree(d.lcol_p); cudaFree(d.roff_p);
-  d.win_meta = nullptr; d.vals_p = nullptr; d.lcol_p = nullptr; d.roff_p = nullptr;
+  cudaFree(d.win_meta); cudaFree(d.blob);
+  d.win_meta = nullptr; d.blob = nullptr;
 }
 
 void free_csr(DevCsr& d) {
@@ -203,25 +201,33 @@ int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* c
   static_assert(sizeof(WinMeta) == sizeof(csb_win::BlockMeta), "meta layout");
   static_assert(W_RB == csb_win::RB && W_WCAP == csb_win::WCAP && W_NNZ == csb_win::NNZ_CAP &&
                 W_MAXSEG == csb_win::MAXSEG, "window geometry");
-  csb_win::Windowed w = csb_win::build(rowptr, colidx, d.nrows, ncols_pad);
+  csb_win::Windowed w = csb_win::build(rowptr, colidx, d.nrows, ncols_pad, (int)sizeof(T));
   d.win_blocks = w.windowed_blocks;
   d.win_nblocks = (int)w.meta.size();
   if (w.windowed_blocks * 2 < (int64_t)w.meta.size()) return CS_B200_OK;   // mostly scattered: keep the plain kernel
   const size_t ne = w.lcol.size();
   int* d_perm = nullptr;
+  int* d_roff_off = nullptr;
+  unsigned short *d_lcol = nullptr, *d_roff = nullptr;
   CK(h, cudaMalloc(&d.win_meta, w.meta.size() * sizeof(WinMeta)));
-  CK(h, cudaMalloc(&d.vals_p, ne * sizeof(T)));
-  CK(h, cudaMalloc(&d.lcol_p, ne * sizeof(unsigned short)));
-  CK(h, cudaMalloc(&d.roff_p, w.roff.size() * sizeof(unsigned short)));
+  CK(h, cudaMalloc(&d.blob, (size_t)w.blob_bytes));
+  CK(h, cudaMalloc(&d_lcol, ne * sizeof(unsigned short)));
+  CK(h, cudaMalloc(&d_roff, w.roff.size() * sizeof(unsigned short)));
+  CK(h, cudaMalloc(&d_roff_off, w.roff_off.size() * sizeof(int)));
   CK(h, cudaMalloc(&d_perm, ne * sizeof(int)));
   CK(h, h2d(h, d.win_meta, w.meta.data(), w.meta.size() * sizeof(WinMeta)));
-  CK(h, h2d(h, d.lcol_p, w.lcol.data(), ne * sizeof(unsigned short)));
-  CK(h, h2d(h, d.roff_p, w.roff.data(), w.roff.size() * sizeof(unsigned short)));
+  CK(h, h2d(h, d_lcol, w.lcol.data(), ne * sizeof(unsigned short)));
+  CK(h, h2d(h, d_roff, w.roff.data(), w.roff.size() * sizeof(unsigned short)));
+  CK(h, h2d(h, d_roff_off, w.roff_off.data(), w.roff_off.size() * sizeof(int)));
   CK(h, h2d(h, d_perm, w.perm_off.data(), ne * sizeof(int)));
-  k_pack_vals<T><<<(int)std::min<size_t>(4096, (ne + 255) / 256), 256, 0, h->stream>>>(
-      ne, d_perm, (const T*)d.vals, (T*)d.vals_p);
+  CK(h, cudaMemsetAsync(d.blob, 0, (size_t)w.blob_bytes, h->stream));
+  k_pack_blob<T><<<std::max(1, std::min(d.win_nblocks, h->num_sms * 16)), 128, 0, h->stream>>>(
+      d.win_nblocks, d.win_meta, d_perm, d_lcol, d_roff, d_roff_off, (const T*)d.vals, d.blob);
   CK(h, cudaGetLastError());
   CK(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_lcol);
+  cudaFree(d_roff);
+  cudaFree(d_roff_off);
   cudaFree(d_perm);
   return CS_B200_OK;
 }
@@ -401,8 +407,7 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
   }
   const SpmmEpi<T> ep{B, dinv, (T)omega, h->d_ctl, h->d_partials};
   if (m.win_meta) {
-    const WinCsr<T> w{m.win_meta, (const T*)m.vals_p, m.lcol_p, m.roff_p, m.rowptr, m.colidx,
-                      (const T*)m.vals, m.win_nblocks};
+    const WinCsr<T> w{m.win_meta, m.blob, m.rowptr, m.colidx, (const T*)m.vals, m.win_nblocks};
     if (m.lpr == 4) {
       constexpr int SMEM = WinSmem2<T, KT, MODE, true>::TOTAL;
       constexpr int SB = WinMap<T, KT, true>::SB;

@@ -453,16 +453,14 @@ constexpr int W_MAXSEG = 8;
 constexpr int W_SMEM_BUDGET = 214 * 1024;   // dynamic shared memory the ring may use
 
 struct WinMeta {                        // == csb_win::BlockMeta
-  int row0, nrows, nnz, ent_off, roff_off, nseg, self_slot, wrows;
+  int row0, nrows, nnz, ent_off, blob_off16, nseg, self_slot, wrows;
   int seg_lo[W_MAXSEG];
   int seg_len[W_MAXSEG];
 };
 
 template <typename T> struct WinCsr {
   const WinMeta* meta;
-  const T* vals_p;
-  const unsigned short* lcol_p;
-  const unsigned short* roff_p;
+  const unsigned char* blob;   // per block: [values | 16-bit local columns | 16-bit row offsets]
   // plain CSR for the direct-gather blocks
   const int* rowptr;
   const int* colidx;
@@ -504,15 +502,11 @@ template <typename T, int KT, int MODE> struct WinSmem {
   static constexpr int al(int x) { return (x + 127) / 128 * 128; }
   static constexpr int XW = al(W_WCAP * KT * (int)sizeof(T));
   static constexpr int BW = NEEDB ? al((W_RB + 8) * KT * (int)sizeof(T)) : 0;
-  static constexpr int VW = al(W_NNZ * (int)sizeof(T));
-  static constexpr int LW = al(W_NNZ * 2);
-  static constexpr int RW = al((W_RB + 8) * 2);
+  static constexpr int VW = al(W_NNZ * ((int)sizeof(T) + 2) + (W_RB + 8) * 2);   // the block's blob
   static constexpr int OFF_X = 0;
   static constexpr int OFF_B = OFF_X + XW;
   static constexpr int OFF_V = OFF_B + BW;
-  static constexpr int OFF_L = OFF_V + VW;
-  static constexpr int OFF_R = OFF_L + LW;
-  static constexpr int STAGE = OFF_R + RW;
+  static constexpr int STAGE = OFF_V + VW;
   static constexpr int NSTAGE = (W_SMEM_BUDGET / STAGE) >= 6 ? 6 : (W_SMEM_BUDGET / STAGE);   // >= 3 for every T, KT
   static constexpr int TOTAL = NSTAGE * STAGE;
 };
@@ -677,15 +671,15 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
           while (!mbar_try_wait(&empty[st], par)) {}
         }
         if (blk >= A.nblocks) {               // tail of the last super-block
-          if (lane == 0) { hdr[st][g] = make_int4(0, 0, 0, -1); mbar_arrive(&full[st]); }
+          if (lane == 0) { hdr[st][g] = make_int4(0, 0, -1, 0); mbar_arrive(&full[st]); }
           continue;
         }
         const int w = wcur[u];
         // meta words: 0 row0, 1 nrows, 2 nnz, 3 ent_off, 4 roff_off, 5 nseg, 6 self_slot, 7 wrows,
         //             8.. seg_lo, 16.. seg_len
         const int row0 = __shfl_sync(0xffffffffu, w, 0), nrows = __shfl_sync(0xffffffffu, w, 1);
-        const int nnz = __shfl_sync(0xffffffffu, w, 2), ent_off = __shfl_sync(0xffffffffu, w, 3);
-        const int roff_off = __shfl_sync(0xffffffffu, w, 4), nseg = __shfl_sync(0xffffffffu, w, 5);
+        const int nnz = __shfl_sync(0xffffffffu, w, 2);
+        const int blob16 = __shfl_sync(0xffffffffu, w, 4), nseg = __shfl_sync(0xffffffffu, w, 5);
         const int self = __shfl_sync(0xffffffffu, w, 6), wrows = __shfl_sync(0xffffffffu, w, 7);
         const int my_lo = __shfl_sync(0xffffffffu, w, 8 + (lane & 7));
         const int my_len = __shfl_sync(0xffffffffu, w, 16 + (lane & 7));
@@ -697,30 +691,29 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
         }
         slot -= (lane < nseg) ? my_len : 0;
         unsigned char* base = dsm + st * S2::STAGE + g * SM::STAGE;
-        if (lane == 0) hdr[st][g] = make_int4(row0, nrows, nseg, self);
+        const int nnzp = (nnz + 7) / 8 * 8;
+        if (lane == 0) hdr[st][g] = make_int4(row0, nrows | (nseg << 16), self, nnzp);
         if (nseg == 0) {
           if (lane == 0) mbar_arrive(&full[st]);
           continue;
         }
-        const int nnzp = (nnz + 7) / 8 * 8;
         const int roffp = (nrows + 1 + 7) / 8 * 8;
         const int b_lo = row0 & ~3;
         const int b_len = ((row0 + nrows + 3) & ~3) - b_lo;
+        const unsigned blob_bytes = (unsigned)(nnzp * ((int)sizeof(T) + 2) + roffp * 2);
         if (lane == 0) {
-          unsigned bytes = (unsigned)(wrows * KT * (int)sizeof(T) + nnzp * (int)sizeof(T) + nnzp * 2 + roffp * 2);
+          unsigned bytes = (unsigned)(wrows * KT * (int)sizeof(T)) + blob_bytes;
           if (SM::NEEDB) bytes += (unsigned)(b_len * KT * (int)sizeof(T));
           mbar_expect_tx(&full[st], bytes);
         }
         __syncwarp();
-        // lanes 0..nseg-1: one X segment each; lanes 8..11: B, values, local columns, row offsets
+        // lanes 0..nseg-1: one X segment each; lane 8: B rows; lane 9: the matrix blob
         if (lane < nseg)
           bulk_g2s(base + SM::OFF_X + (size_t)slot * KT * sizeof(T), X + (size_t)my_lo * KT,
                    (unsigned)(my_len * KT * (int)sizeof(T)), &full[st]);
         if (SM::NEEDB && lane == 8)
           bulk_g2s(base + SM::OFF_B, ep.B + (size_t)b_lo * KT, (unsigned)(b_len * KT * (int)sizeof(T)), &full[st]);
-        if (lane == 9) bulk_g2s(base + SM::OFF_V, A.vals_p + ent_off, (unsigned)(nnzp * (int)sizeof(T)), &full[st]);
-        if (lane == 10) bulk_g2s(base + SM::OFF_L, A.lcol_p + ent_off, (unsigned)(nnzp * 2), &full[st]);
-        if (lane == 11) bulk_g2s(base + SM::OFF_R, A.roff_p + roff_off, (unsigned)(roffp * 2), &full[st]);
+        if (lane == 9) bulk_g2s(base + SM::OFF_V, A.blob + (size_t)blob16 * 16, blob_bytes, &full[st]);
       }
 #pragma unroll
       for (int u = 0; u < PD; ++u) wcur[u] = wnxt[u];
@@ -736,14 +729,14 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
       const int st = it % NS;
       while (!mbar_try_wait(&full[st], (unsigned)((it / NS) & 1))) {}
       const int4 h = hdr[st][g];
-      const int row0 = h.x, nr = h.y, nseg = h.z, self = h.w;
+      const int row0 = h.x, nr = h.y & 0xffff, nseg = h.y >> 16, self = h.z, nnzp = h.w;
       if (nseg > 0) {
         const unsigned char* base = dsm + st * S2::STAGE + g * SM::STAGE;
         const T* xw = reinterpret_cast<const T*>(base + SM::OFF_X);
         const T* bw = reinterpret_cast<const T*>(base + SM::OFF_B);
         const T* vw = reinterpret_cast<const T*>(base + SM::OFF_V);
-        const unsigned short* lw = reinterpret_cast<const unsigned short*>(base + SM::OFF_L);
-        const unsigned short* rw = reinterpret_cast<const unsigned short*>(base + SM::OFF_R);
+        const unsigned short* lw = reinterpret_cast<const unsigned short*>(vw + nnzp);
+        const unsigned short* rw = lw + nnzp;
         const int b_lo = row0 & ~3;
         for (int basei = 0; basei < nr; basei += RPP) {
           const int rl = basei + gt / LPRW;
@@ -854,7 +847,7 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
 #pragma unroll
       for (int q = 0; q < SB; ++q) {
         const int4 hq = hdr[st][q];
-        any_long |= (hq.z == 0 && hq.y == 1 && (A.rowptr[hq.x + 1] - A.rowptr[hq.x]) > W_NNZ);
+        any_long |= (hq.y == 1 && (A.rowptr[hq.x + 1] - A.rowptr[hq.x]) > W_NNZ);   // nseg 0, one row
       }
       if (any_long) {
         consumer_sync();
@@ -908,13 +901,30 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
   }
 }
 
-// packed values of the windowed form:  vals_p[i] = perm[i] >= 0 ? vals[perm[i]] : 0
+// Build the per-block records of the windowed form on the device: one CTA per block copies
+// the values (through the host-built permutation), the 16-bit local columns and the row
+// offsets into  blob + blob_off16*16 :  [ values nnzp | lcol nnzp | roff roffp ].
 template <typename T>
-__global__ void k_pack_vals(size_t n, const int* __restrict__ perm, const T* __restrict__ vals,
-                            T* __restrict__ out) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int p = perm[i];
-    out[i] = p >= 0 ? vals[p] : T(0);
+__global__ void k_pack_blob(int nblocks, const WinMeta* __restrict__ meta, const int* __restrict__ perm,
+                            const unsigned short* __restrict__ lcol, const unsigned short* __restrict__ roff,
+                            const int* __restrict__ roff_off, const T* __restrict__ vals,
+                            unsigned char* __restrict__ blob) {
+  for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const WinMeta m = meta[b];
+    if (m.nseg == 0) continue;
+    const int nnzp = (m.nnz + 7) / 8 * 8;
+    const int roffp = (m.nrows + 1 + 7) / 8 * 8;
+    unsigned char* rec = blob + (size_t)m.blob_off16 * 16;
+    T* v = reinterpret_cast<T*>(rec);
+    unsigned short* lc = reinterpret_cast<unsigned short*>(v + nnzp);
+    unsigned short* ro = lc + nnzp;
+    for (int i = threadIdx.x; i < nnzp; i += blockDim.x) {
+      const int p = perm[(size_t)m.ent_off + i];
+      v[i] = p >= 0 ? vals[p] : T(0);
+      lc[i] = lcol[(size_t)m.ent_off + i];
+    }
+    const int r0 = roff_off[b];
+    for (int i = threadIdx.x; i < roffp; i += blockDim.x) ro[i] = i <= m.nrows ? roff[(size_t)r0 + i] : (unsigned short)0;
   }
 }
 

@@ -27,7 +27,8 @@ struct BlockMeta {             // 96 bytes, one per row block (device + host ide
   int row0, nrows;
   int nnz;                     // entries of the block
   int ent_off;                 // first entry in vals_p / lcol_p (multiple of 8)
-  int roff_off;                // first entry in roff_p (multiple of 8)
+  int blob_off16;              // byte offset / 16 of the block's record in the packed blob:
+                               //   [ values nnzp*sizeof(T) | local cols nnzp*2 | row offsets roffp*2 ]
   int nseg;                    // 0 => direct-gather path
   int self_slot;               // window slot of X[row0] if rows row0.. are contiguous in it, else -1
   int wrows;                   // total staged X rows
@@ -40,7 +41,9 @@ struct Windowed {
   std::vector<uint16_t> lcol;   // packed, per block padded to 8
   std::vector<int> perm_off;    // per packed entry: index into the CSR value array or -1 (padding)
   std::vector<uint16_t> roff;   // packed row offsets (nrows+1 per block, padded to 8)
+  std::vector<int> roff_off;    // per block: first entry in roff
   int64_t windowed_blocks = 0;
+  int64_t blob_bytes = 0;       // size of the device blob for value size `vsize`
 };
 
 // greedy row blocks of the windowed form: <= RB rows and <= NNZ_CAP entries; a longer row
@@ -59,7 +62,8 @@ inline std::vector<int> row_blocks(const int* rowptr, int64_t n) {
 }
 
 inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
-                      int64_t ncols_pad /* X rows available (n_pad of the input panel) */) {
+                      int64_t ncols_pad /* X rows available (n_pad of the input panel) */,
+                      int vsize = 8 /* sizeof(T) of the device values */) {
   Windowed w;
   const std::vector<int> bstart = row_blocks(rowptr, nrows);
   const int nb = (int)bstart.size() - 1;
@@ -73,6 +77,19 @@ inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
     ent_off[b + 1] = ent_off[b] + (fits ? (cnt + 7) / 8 * 8 : 0);
     roff_off[b + 1] = roff_off[b] + (fits ? (r1 - r0 + 1 + 7) / 8 * 8 : 0);
   }
+  w.roff_off.resize(nb);
+  {
+    int64_t bo = 0;   // blob offsets (bytes, multiples of 16)
+    for (int b = 0; b < nb; ++b) {
+      const int r0 = bstart[b], r1 = bstart[b + 1];
+      const int cnt = rowptr[r1] - rowptr[r0];
+      const bool fits = cnt <= NNZ_CAP && (r1 - r0) <= RB;
+      w.meta[b].blob_off16 = (int)(bo / 16);
+      w.roff_off[b] = (int)roff_off[b];
+      if (fits) bo += (int64_t)((cnt + 7) / 8 * 8) * (vsize + 2) + (int64_t)((r1 - r0 + 1 + 7) / 8 * 8) * 2;
+    }
+    w.blob_bytes = bo + 64;
+  }
   w.lcol.assign((size_t)ent_off[nb] + 8, 0);
   w.perm_off.assign((size_t)ent_off[nb] + 8, -1);
   w.roff.assign((size_t)roff_off[nb] + 8, 0);
@@ -82,9 +99,12 @@ inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
     BlockMeta& m = w.meta[b];
     const int r0 = bstart[b], r1 = bstart[b + 1];
     const int s = rowptr[r0], e = rowptr[r1];
+    const int keep_blob = m.blob_off16;
     m = BlockMeta{};
+    m.blob_off16 = keep_blob;
     m.row0 = r0; m.nrows = r1 - r0; m.nnz = e - s;
-    m.ent_off = (int)ent_off[b]; m.roff_off = (int)roff_off[b];
+    m.ent_off = (int)ent_off[b];
+    const int my_roff = (int)roff_off[b];
     m.nseg = 0; m.self_slot = -1; m.wrows = 0;
     if (m.nnz > NNZ_CAP || m.nrows > RB || m.nnz == 0) continue;
     // unique sorted columns of the block
@@ -126,7 +146,7 @@ inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
       w.lcol[(size_t)m.ent_off + (j - s)] = (uint16_t)(off[k] + (c - lo[k]));
       w.perm_off[(size_t)m.ent_off + (j - s)] = j;
     }
-    for (int r = r0; r <= r1; ++r) w.roff[(size_t)m.roff_off + (r - r0)] = (uint16_t)(rowptr[r] - s);
+    for (int r = r0; r <= r1; ++r) w.roff[(size_t)my_roff + (r - r0)] = (uint16_t)(rowptr[r] - s);
     // are the block's own rows one contiguous stretch of the window?
     for (int k = 0; k < nseg; ++k)
       if (r0 >= lo[k] && r1 <= lo[k] + len[k]) { m.self_slot = off[k] + (r0 - lo[k]); break; }

@@ -65,9 +65,10 @@ extern "C" long winh_spmv_rect(long n, long ncols, long nnz, const int* ptr, con
       for (int i = 0; i < m.seg_len[k]; ++i) win[slot + i] = xp[m.seg_lo[k] + i];
       slot += m.seg_len[k];
     }
-    if (slot != m.wrows || m.ent_off % 8 || m.roff_off % 8) return -2;
+    if (slot != m.wrows || m.ent_off % 8 || w.roff_off[&m - w.meta.data()] % 8 || m.blob_off16 < 0) return -2;
     for (int rl = 0; rl < m.nrows; ++rl) {
-      const int a = w.roff[m.roff_off + rl], b = w.roff[m.roff_off + rl + 1];
+      const int ro = w.roff_off[&m - w.meta.data()];
+      const int a = w.roff[ro + rl], b = w.roff[ro + rl + 1];
       double s = 0;
       for (int j = a; j < b; ++j) {
         const int p = w.perm_off[m.ent_off + j];
