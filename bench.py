@@ -294,9 +294,14 @@ def main():
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall, res
 
+    # clocks are sampled from the first warm-up step to the end of the timed region (the
+    # timed region alone can be shorter than nvidia-smi's start-up + sampling period)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local) if rank == 0 else None
+    t_w = time.time()
+    while rank == 0 and sampler and len(sampler.lines) < 2 and time.time() - t_w < 3.0:
+        step()                                # keep the GPU under load until samples arrive
     ms, wall, res = timed(step, args.steps)
     clocks = sampler.stop() if sampler else None
     R, out, st = res[-1]

@@ -136,14 +136,15 @@ cudaError_t h2d(cs_b200_handle* h, void* dst, const void* src, size_t bytes) {
 int kt_index(int kt) { return kt == 1 ? 0 : kt == 2 ? 1 : kt == 4 ? 2 : 3; }
 
 // greedy row blocks: <= NNZ_CAP nnz and <= NT rows; an over-long row stands alone.
-void build_row_blocks(const std::vector<int>& rowptr, int64_t n, std::vector<int>& bstart) {
+void build_row_blocks(const std::vector<int>& rowptr, int64_t n, std::vector<int>& bstart,
+                      int max_rows = NT) {
   bstart.clear();
   bstart.push_back(0);
   int64_t r = 0;
   while (r < n) {
     int64_t r1 = r + 1;
     const int64_t base = rowptr[r];
-    while (r1 < n && (r1 - r) < NT && (int64_t)rowptr[r1 + 1] - base <= NNZ_CAP) ++r1;
+    while (r1 < n && (r1 - r) < max_rows && (int64_t)rowptr[r1 + 1] - base <= NNZ_CAP) ++r1;
     bstart.push_back((int)r1);
     r = r1;
   }
@@ -163,10 +164,15 @@ template <typename T>
 int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowed) {
   d.nrows = (int)m.nrows;
   d.nnz = m.nnz();
-  std::vector<int> bstart;
-  build_row_blocks(m.ptr, m.nrows, bstart);
-  d.nblocks = (int)bstart.size() - 1;
   d.lpr = (m.nrows > 0 && (double)d.nnz / (double)m.nrows >= 20.0) ? 4 : 1;
+  // small operators (coarse levels): shrink the row blocks so that >= 4 CTAs per SM exist --
+  // their kernels are latency-bound chains of dependent gathers, not bandwidth-bound
+  const int unit = d.lpr == 4 ? 8 : 32;          // rows per pass of k_spmm at KT = 8
+  int max_rows = (int)((m.nrows + 4 * h->num_sms - 1) / (4 * h->num_sms));
+  max_rows = std::min(NT, std::max(unit, (max_rows + unit - 1) / unit * unit));
+  std::vector<int> bstart;
+  build_row_blocks(m.ptr, m.nrows, bstart, max_rows);
+  d.nblocks = (int)bstart.size() - 1;
   std::vector<T> v(m.val.begin(), m.val.end());
   CK(h, cudaMalloc(&d.rowptr, (size_t)(m.nrows + 1) * sizeof(int)));
   CK(h, cudaMalloc(&d.colidx, std::max<size_t>(1, (size_t)d.nnz) * sizeof(int)));
@@ -199,9 +205,10 @@ void free_csr(DevCsr& d) {
 template <typename T>
 int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx, int64_t ncols_pad) {
   static_assert(sizeof(WinMeta) == sizeof(csb_win::BlockMeta), "meta layout");
-  static_assert(W_RB == csb_win::RB && W_WCAP == csb_win::WCAP && W_NNZ == csb_win::NNZ_CAP &&
+  static_assert(W_RB == csb_win::RB && W_WCAP == csb_win::WCAP && W_WCAP_WIDE == csb_win::WCAP_WIDE && W_NNZ == csb_win::NNZ_CAP &&
                 W_MAXSEG == csb_win::MAXSEG, "window geometry");
-  csb_win::Windowed w = csb_win::build(rowptr, colidx, d.nrows, ncols_pad, (int)sizeof(T));
+  csb_win::Windowed w = csb_win::build(rowptr, colidx, d.nrows, ncols_pad, (int)sizeof(T),
+                                       d.lpr == 4 ? csb_win::WCAP_WIDE : csb_win::WCAP);
   d.win_blocks = w.windowed_blocks;
   d.win_nblocks = (int)w.meta.size();
   if (w.windowed_blocks * 2 < (int64_t)w.meta.size()) return CS_B200_OK;   // mostly scattered: keep the plain kernel
@@ -469,7 +476,7 @@ int ew_grid_n(cs_b200_handle* h, int64_t n_pad) {
 // Level buffers: b = right-hand side, x = running correction, t = residual scratch,
 // y = post-smoothed correction.  Finest level: b = R, x = stage, t = AP, y = Z.
 template <typename T, int KT>
-void launch_vcycle(cs_b200_handle* h) {
+void launch_vcycle(cs_b200_handle* h, bool level0_presmoothed) {
   const int nl = (int)h->lv.size();
   auto B = [&](int l) { return l == 0 ? (T*)h->R : (T*)h->lv[l].b; };
   auto X = [&](int l) { return l == 0 ? (T*)h->stage : (T*)h->lv[l].x; };
@@ -478,9 +485,11 @@ void launch_vcycle(cs_b200_handle* h) {
   for (int l = 0; l < nl - 1; ++l) {
     DevLevel& L = h->lv[l];
     const size_t nelem = (size_t)L.n_pad * KT;
-    k_jacobi0<T, KT><<<ew_grid_n<T, KT>(h, L.n_pad), NT, 0, h->stream>>>(
-        nelem, B(l), (const T*)L.dinv, (T)L.omega, X(l));
-    h->stats.kernel_launches++;
+    if (!(l == 0 && level0_presmoothed)) {
+      k_jacobi0<T, KT><<<ew_grid_n<T, KT>(h, L.n_pad), NT, 0, h->stream>>>(
+          nelem, B(l), (const T*)L.dinv, (T)L.omega, X(l));
+      h->stats.kernel_launches++;
+    }
     launch_spmm_on<T, KT, SP_RES>(h, L.A, X(l), Tm(l), B(l), nullptr, 0.0, l == 0);
     launch_spmm_on<T, KT, SP_PLAIN>(h, L.R, Tm(l), B(l + 1), nullptr, nullptr, 0.0, false);
   }
@@ -521,10 +530,12 @@ void launch_iteration(cs_b200_handle* h) {
                                                    (T*)h->X, (T*)h->P, h->d_ctl);
     h->stats.kernel_launches += 2;
   } else {
-    k_cg_update_xr<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->P, (const T*)h->AP, (T*)h->X,
-                                                   (T*)h->R, h->d_ctl);
-    launch_vcycle<T, KT>(h);
-    k_cg_update_p<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->P, h->d_ctl);
+    // r -= alpha Ap with the finest pre-smoothing folded in; V-cycle; then the deferred
+    // x += alpha p together with p = z + beta p  (9 instead of 11 panel passes)
+    k_cg_update_r0<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->AP, (const T*)h->d_dinv,
+                                                   (T)h->lv[0].omega, (T*)h->R, (T*)h->stage, h->d_ctl);
+    launch_vcycle<T, KT>(h, true);
+    k_cg_update_xp2<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->X, (T*)h->P, h->d_ctl);
     h->stats.kernel_launches += 2;
   }
 }
@@ -584,8 +595,8 @@ int solve_panel(cs_b200_handle* h, double rtol, int64_t itmax) {
     CK(h, cudaMemsetAsync(h->P, 0, nelem * sizeof(T), h->stream));
     CK(h, cudaMemcpyAsync(h->R, h->B, nelem * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
     k_set_ctl<<<1, 1, 0, h->stream>>>(h->d_ctl, rtol, atol, imax);
-    launch_vcycle<T, KT>(h);
-    k_cg_update_p<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->P, h->d_ctl);
+    launch_vcycle<T, KT>(h, false);
+    k_cg_update_xp2<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->X, (T*)h->P, h->d_ctl);
     h->stats.kernel_launches += 2;
   }
   CK(h, cudaGetLastError());

@@ -449,6 +449,7 @@ k_spmm(const CsrDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const Spmm
 constexpr int W_RB = 128;               // == csb_win::RB
 constexpr int W_NNZ = 1152;             // == csb_win::NNZ_CAP
 constexpr int W_WCAP = 512;             // == csb_win::WCAP
+constexpr int W_WCAP_WIDE = 1024;       // == csb_win::WCAP_WIDE
 constexpr int W_MAXSEG = 8;
 constexpr int W_SMEM_BUDGET = 214 * 1024;   // dynamic shared memory the ring may use
 
@@ -496,11 +497,11 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
   return ok != 0;
 }
 
-template <typename T, int KT, int MODE> struct WinSmem {
+template <typename T, int KT, int MODE, bool WIDE = false> struct WinSmem {
   static constexpr bool NEEDB = (MODE == SP_RESNORM || MODE == SP_RES || MODE == SP_JACOBI ||
                                  MODE == SP_JACOBI_DOT);
   static constexpr int al(int x) { return (x + 127) / 128 * 128; }
-  static constexpr int XW = al(W_WCAP * KT * (int)sizeof(T));
+  static constexpr int XW = al((WIDE ? W_WCAP_WIDE : W_WCAP) * KT * (int)sizeof(T));
   static constexpr int BW = NEEDB ? al((W_RB + 8) * KT * (int)sizeof(T)) : 0;
   static constexpr int VW = al(W_NNZ * ((int)sizeof(T) + 2) + (W_RB + 8) * 2);   // the block's blob
   static constexpr int OFF_X = 0;
@@ -596,7 +597,7 @@ template <typename T, int KT, bool WIDE> struct WinMap {
 };
 
 template <typename T, int KT, int MODE, bool WIDE> struct WinSmem2 {
-  using S1 = WinSmem<T, KT, MODE>;
+  using S1 = WinSmem<T, KT, MODE, WIDE>;
   static constexpr int SB = WinMap<T, KT, WIDE>::SB;
   static constexpr int STAGE = S1::STAGE * SB;
   static constexpr int NSTAGE = (W_SMEM_BUDGET / STAGE) >= 6 ? 6 : (W_SMEM_BUDGET / STAGE);
@@ -606,7 +607,7 @@ template <typename T, int KT, int MODE, bool WIDE> struct WinSmem2 {
 template <typename T, int KT, int MODE, bool WIDE>
 __global__ void __launch_bounds__(WTT, 1)
 k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
-  using SM = WinSmem<T, KT, MODE>;
+  using SM = WinSmem<T, KT, MODE, WIDE>;
   using S2 = WinSmem2<T, KT, MODE, WIDE>;
   using MP = WinMap<T, KT, WIDE>;
   constexpr int NS = S2::NSTAGE;
@@ -1066,49 +1067,58 @@ k_cg_update_xp(size_t nelem, const T* __restrict__ R, const T* __restrict__ dinv
   }
 }
 
-// AMG-PCG:  X += alpha*P ;  R -= alpha*AP   (z and rho come from the V-cycle)
+// AMG-PCG, after the SpMM:  R -= alpha*AP ;  X0 = omega * Dinv * R   (the zero-guess
+// pre-smoothing sweep of the finest level is folded in: one pass fewer over R)
 template <typename T, int KT>
 __global__ void __launch_bounds__(NT)
-k_cg_update_xr(size_t nelem, const T* __restrict__ P, const T* __restrict__ AP, T* __restrict__ X,
-               T* __restrict__ R, const PanelCtl* ctl) {
+k_cg_update_r0(size_t nelem, const T* __restrict__ AP, const T* __restrict__ dinv, T omega,
+               T* __restrict__ R, T* __restrict__ X0, const PanelCtl* ctl) {
   constexpr int VEC = Vec<T>::N;
+  constexpr int L = Log2<KT>::v;
   const size_t e0 = ((size_t)blockIdx.x * NT + threadIdx.x) * VEC;
   const size_t stride = (size_t)gridDim.x * NT * VEC;
   T al[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) al[i] = (T)ctl->alpha[(e0 + i) % KT];
   for (size_t e = e0; e < nelem; e += stride) {
-    T p[VEC], ap[VEC], x[VEC], r[VEC];
-    vload(P + e, p);
+    T ap[VEC], r[VEC], x0[VEC];
     vload(AP + e, ap);
-    vload(X + e, x);
     vload(R + e, r);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      x[i] += al[i] * p[i];
       r[i] -= al[i] * ap[i];
+      x0[i] = omega * dinv[(e + i) >> L] * r[i];
     }
-    vstore(X + e, x);
     vstore(R + e, r);
+    vstore(X0 + e, x0);
   }
 }
 
-// AMG-PCG:  P = Z + beta*P
+// AMG-PCG, after the V-cycle:  X += alpha*P (the deferred solution update) ;  P = Z + beta*P
 template <typename T, int KT>
 __global__ void __launch_bounds__(NT)
-k_cg_update_p(size_t nelem, const T* __restrict__ Z, T* __restrict__ P, const PanelCtl* ctl) {
+k_cg_update_xp2(size_t nelem, const T* __restrict__ Z, T* __restrict__ X, T* __restrict__ P,
+                const PanelCtl* ctl) {
   constexpr int VEC = Vec<T>::N;
   const size_t e0 = ((size_t)blockIdx.x * NT + threadIdx.x) * VEC;
   const size_t stride = (size_t)gridDim.x * NT * VEC;
-  T be[VEC];
+  T al[VEC], be[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) be[i] = (T)ctl->beta[(e0 + i) % KT];
+  for (int i = 0; i < VEC; ++i) {
+    al[i] = (T)ctl->alpha[(e0 + i) % KT];
+    be[i] = (T)ctl->beta[(e0 + i) % KT];
+  }
   for (size_t e = e0; e < nelem; e += stride) {
-    T z[VEC], p[VEC];
+    T z[VEC], p[VEC], x[VEC];
     vload(Z + e, z);
     vload(P + e, p);
+    vload(X + e, x);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) p[i] = z[i] + be[i] * p[i];
+    for (int i = 0; i < VEC; ++i) {
+      x[i] += al[i] * p[i];
+      p[i] = z[i] + be[i] * p[i];
+    }
+    vstore(X + e, x);
     vstore(P + e, p);
   }
 }

@@ -19,6 +19,7 @@ namespace csb_win {
 constexpr int RB = 128;        // rows per block
 constexpr int NNZ_CAP = 1152;  // entries per block (128 rows x 9)
 constexpr int WCAP = 512;      // X rows staged per block (all segments together)
+constexpr int WCAP_WIDE = 1024; // ... for wide-row operators (restrictions)
 constexpr int MAXSEG = 8;
 constexpr int ALN = 4;         // segment start/length granularity in X rows (16 B at KT=1, fp32)
 constexpr int MERGE_GAP = 16;  // runs closer than this are merged into one segment
@@ -63,7 +64,7 @@ inline std::vector<int> row_blocks(const int* rowptr, int64_t n) {
 
 inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
                       int64_t ncols_pad /* X rows available (n_pad of the input panel) */,
-                      int vsize = 8 /* sizeof(T) of the device values */) {
+                      int vsize = 8 /* sizeof(T) of the device values */, int wcap = WCAP) {
   Windowed w;
   const std::vector<int> bstart = row_blocks(rowptr, nrows);
   const int nb = (int)bstart.size() - 1;
@@ -133,7 +134,7 @@ inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
       }
       i = j;
     }
-    if (!ok || total > WCAP) continue;
+    if (!ok || total > wcap) continue;
     m.nseg = nseg; m.wrows = total;
     int off[MAXSEG];
     int acc = 0;

@@ -45,10 +45,11 @@ extern "C" long winh_spmv_rect(long n, long ncols, long nnz, const int* ptr, con
   const long n_pad = (ncols + 3) / 4 * 4;
   std::vector<double> xp(n_pad, 0.0);
   std::memcpy(xp.data(), x, ncols * sizeof(double));
-  csb_win::Windowed w = csb_win::build(ptr, idx, n, n_pad);
+  const int wcap = (double)nnz / (double)n >= 20.0 ? csb_win::WCAP_WIDE : csb_win::WCAP;   // as cs_b200.cu
+  csb_win::Windowed w = csb_win::build(ptr, idx, n, n_pad, 8, wcap);
   *nblocks = (long)w.meta.size();
   *max_wrows = 0;
-  std::vector<double> win(csb_win::WCAP);
+  std::vector<double> win(csb_win::WCAP_WIDE);
   for (const auto& m : w.meta) {
     if (m.nseg == 0) {
       for (int row = m.row0; row < m.row0 + m.nrows; ++row) {
