@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--cols", type=int, default=1000)
     ap.add_argument("--pairs-per-gpu", type=int, default=10)
     ap.add_argument("--precision", default="double")
-    ap.add_argument("--precond", default="jacobi")
+    ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"])
     ap.add_argument("--rtol", type=float, default=1e-6)
     ap.add_argument("--skip-spmv1e7", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -44,7 +44,7 @@ def get_solver(cfg):
         precision=cfg.get("precision", "double"),
         device=int(cfg.get("gpu_device", "0")),
         rtol=float(cfg.get("gpu_rtol", "1e-6")),
-        precond=cfg.get("gpu_preconditioner", "jacobi"),
+        precond=cfg.get("gpu_preconditioner", "amg"),
     )
 
 

@@ -35,7 +35,7 @@ class CUDASolver:
     device: int = 0
     rtol: float = 1e-6               # src/core.jl:639
     itmax: int = 100_000             # src/core.jl:639
-    precond: str = "jacobi"
+    precond: str = "amg"             # "amg" (smoothed aggregation V-cycle) | "jacobi"
     panel_width: int = 8
     check_every: int = 16
     use_graph: bool = True
