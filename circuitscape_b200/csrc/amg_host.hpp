@@ -272,6 +272,11 @@ inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 9
     Csr R = transpose(P);
     Csr AP = spgemm(lv.A, P);
     Csr Ac = spgemm(R, AP);
+    // expander-like graphs (power-law networks) densify under smoothed aggregation: a coarse
+    // operator with more entries than the one it came from buys nothing on a bandwidth-bound
+    // machine -- stop here (the cycle ends at this level; with no level at all the solver is
+    // plain Jacobi-PCG)
+    if (Ac.nnz() > lv.A.nnz()) break;
     lv.P = std::move(P);
     lv.R = std::move(R);
     h.levels.emplace_back();
