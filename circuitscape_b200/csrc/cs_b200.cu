@@ -45,7 +45,8 @@ struct DevCsr {
   int lpr = 1;  // lanes per row used by k_spmm for this matrix
   // windowed row-block form for the TMA-staged kernel (win_host.hpp); null => plain kernel
   WinMeta* win_meta = nullptr;
-  unsigned char* blob = nullptr;   // per-block records [values | local columns | row offsets]
+  unsigned char* blob = nullptr;   // per-block records [values | 1/diag | local columns | row offsets]
+  int has_dinv = 0;
   int64_t win_blocks = 0;
   int win_nblocks = 0;
 };
@@ -151,7 +152,8 @@ void build_row_blocks(const std::vector<int>& rowptr, int64_t n, std::vector<int
 }
 
 template <typename T>
-int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx, int64_t ncols_pad);
+int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx, int64_t ncols_pad,
+                   const T* d_dinv = nullptr);
 
 // upload one host CSR (double values) as a device CSR of T with its row blocks
 // debugging aid: CS_B200_WIN_MASK bit 0 = finest A, 1 = coarse A, 2 = P, 3 = R (default all)
@@ -161,7 +163,7 @@ int win_mask() {
 }
 
 template <typename T>
-int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowed) {
+int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowed, const T* d_dinv = nullptr) {
   d.nrows = (int)m.nrows;
   d.nnz = m.nnz();
   d.lpr = (m.nrows > 0 && (double)d.nnz / (double)m.nrows >= 20.0) ? 4 : 1;
@@ -184,7 +186,7 @@ int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowe
   CK(h, h2d(h, d.bstart, bstart.data(), bstart.size() * sizeof(int)));
   if (h->opts.window >= 0 && windowed) {
     const int64_t ncols_pad = (m.ncols + 3) / 4 * 4;
-    return build_windowed<T>(h, d, m.ptr.data(), m.idx.data(), ncols_pad);
+    return build_windowed<T>(h, d, m.ptr.data(), m.idx.data(), ncols_pad, d_dinv);
   }
   return CS_B200_OK;
 }
@@ -203,12 +205,14 @@ void free_csr(DevCsr& d) {
 // Build + upload the windowed row-block form of a CSR already resident in `d`.
 // rowptr/colidx: host copies; ncols_pad: rows of the input panel (n_pad of the column space).
 template <typename T>
-int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx, int64_t ncols_pad) {
+int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* colidx, int64_t ncols_pad,
+                   const T* d_dinv) {
   static_assert(sizeof(WinMeta) == sizeof(csb_win::BlockMeta), "meta layout");
   static_assert(W_RB == csb_win::RB && W_WCAP == csb_win::WCAP && W_WCAP_WIDE == csb_win::WCAP_WIDE && W_NNZ == csb_win::NNZ_CAP &&
                 W_MAXSEG == csb_win::MAXSEG, "window geometry");
   csb_win::Windowed w = csb_win::build(rowptr, colidx, d.nrows, ncols_pad, (int)sizeof(T),
-                                       d.lpr == 4 ? csb_win::WCAP_WIDE : csb_win::WCAP);
+                                       d.lpr == 4 ? csb_win::WCAP_WIDE : csb_win::WCAP, d_dinv != nullptr);
+  d.has_dinv = d_dinv != nullptr ? 1 : 0;
   d.win_blocks = w.windowed_blocks;
   d.win_nblocks = (int)w.meta.size();
   if (w.windowed_blocks * 2 < (int64_t)w.meta.size()) return CS_B200_OK;   // mostly scattered: keep the plain kernel
@@ -229,7 +233,7 @@ int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* c
   CK(h, h2d(h, d_perm, w.perm_off.data(), ne * sizeof(int)));
   CK(h, cudaMemsetAsync(d.blob, 0, (size_t)w.blob_bytes, h->stream));
   k_pack_blob<T><<<std::max(1, std::min(d.win_nblocks, h->num_sms * 16)), 128, 0, h->stream>>>(
-      d.win_nblocks, d.win_meta, d_perm, d_lcol, d_roff, d_roff_off, (const T*)d.vals, d.blob);
+      d.win_nblocks, d.win_meta, d_perm, d_lcol, d_roff, d_roff_off, (const T*)d.vals, d_dinv, d.blob);
   CK(h, cudaGetLastError());
   CK(h, cudaStreamSynchronize(h->stream));
   cudaFree(d_lcol);
@@ -262,12 +266,12 @@ int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<i
       L.A = h->A0;  // alias, not owned
       L.dinv = h->d_dinv;
     } else {
-      int rc = upload_csr<T>(h, hl.A, L.A, L.n >= 20000 && (win_mask() & 2));
-      if (rc) return rc;
       std::vector<T> dv(L.n_pad, T(0));
       for (int64_t i = 0; i < L.n; ++i) dv[i] = (T)hl.dinv[i];
       CK(h, cudaMalloc(&L.dinv, (size_t)L.n_pad * sizeof(T)));
       CK(h, h2d(h, L.dinv, dv.data(), (size_t)L.n_pad * sizeof(T)));
+      int rc = upload_csr<T>(h, hl.A, L.A, L.n >= 20000 && (win_mask() & 2), (const T*)L.dinv);
+      if (rc) return rc;
       const size_t pe = (size_t)L.n_pad * h->ktmax * sizeof(T);
       void** bufs[] = {&L.x, &L.b, &L.t, &L.y};
       for (void** bp : bufs) {
@@ -337,7 +341,7 @@ int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std:
     }
   }
   if (want_win) {
-    int rc = build_windowed<T>(h, h->A0, h_rowptr.data(), h_colidx->data(), h->n_pad);
+    int rc = build_windowed<T>(h, h->A0, h_rowptr.data(), h_colidx->data(), h->n_pad, (const T*)h->d_dinv);
     if (rc) return rc;
   }
   if (want_amg) {
@@ -414,7 +418,7 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
   }
   const SpmmEpi<T> ep{B, dinv, (T)omega, h->d_ctl, h->d_partials};
   if (m.win_meta) {
-    const WinCsr<T> w{m.win_meta, m.blob, m.rowptr, m.colidx, (const T*)m.vals, m.win_nblocks};
+    const WinCsr<T> w{m.win_meta, m.blob, m.has_dinv, m.rowptr, m.colidx, (const T*)m.vals, m.win_nblocks};
     if (m.lpr == 4) {
       constexpr int SMEM = WinSmem2<T, KT, MODE, true>::TOTAL;
       constexpr int SB = WinMap<T, KT, true>::SB;
@@ -510,7 +514,7 @@ void launch_vcycle(cs_b200_handle* h, bool level0_presmoothed) {
   }
   for (int l = nl - 2; l >= 0; --l) {
     DevLevel& L = h->lv[l];
-    launch_spmm_on<T, KT, SP_ADD>(h, L.P, Y(l + 1), X(l), nullptr, nullptr, 0.0, false);
+    launch_spmm_on<T, KT, SP_ADD>(h, L.P, Y(l + 1), X(l), X(l) /* staged as B */, nullptr, 0.0, false);
     if (l == 0)
       launch_spmm_on<T, KT, SP_JACOBI_DOT>(h, L.A, X(l), Y(l), B(l), (const T*)L.dinv, L.omega, true);
     else
@@ -584,6 +588,7 @@ int solve_panel(cs_b200_handle* h, double rtol, int64_t itmax) {
   const int imax = (int)std::min<int64_t>(itmax, std::numeric_limits<int>::max() - 1);
   CK(h, cudaEventRecord(h->ev2, h->stream));
   if (!h->amg) {
+    k_set_stall<<<1, 1, 0, h->stream>>>(h->d_ctl, 2000);
     k_cg_init<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->B, (const T*)h->d_dinv, (T*)h->X,
                                               (T*)h->R, (T*)h->P, h->d_ctl, h->d_partials, rtol, atol,
                                               imax);
@@ -594,7 +599,7 @@ int solve_panel(cs_b200_handle* h, double rtol, int64_t itmax) {
     CK(h, cudaMemsetAsync(h->X, 0, nelem * sizeof(T), h->stream));
     CK(h, cudaMemsetAsync(h->P, 0, nelem * sizeof(T), h->stream));
     CK(h, cudaMemcpyAsync(h->R, h->B, nelem * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
-    k_set_ctl<<<1, 1, 0, h->stream>>>(h->d_ctl, rtol, atol, imax);
+    k_set_ctl<<<1, 1, 0, h->stream>>>(h->d_ctl, rtol, atol, imax, 40);
     launch_vcycle<T, KT>(h, false);
     k_cg_update_xp2<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->X, (T*)h->P, h->d_ctl);
     h->stats.kernel_launches += 2;
@@ -1046,8 +1051,8 @@ int cs_b200_spmm(cs_b200_handle* h, int k, const void* x, void* y) {
   else { DISPATCH_KT(k, (k_cm_to_panel<float, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const float*)h->stage, (float*)h->X, KT))); }
   if (add) {
     CK(h, cudaMemcpyAsync(h->AP, h->X, nelem * h->esize(), cudaMemcpyDeviceToDevice, h->stream));
-    if (f64) { DISPATCH_KT(k, (launch_spmm<double, KT, SP_ADD>(h, (const double*)h->X, (double*)h->AP, nullptr))); }
-    else { DISPATCH_KT(k, (launch_spmm<float, KT, SP_ADD>(h, (const float*)h->X, (float*)h->AP, nullptr))); }
+    if (f64) { DISPATCH_KT(k, (launch_spmm<double, KT, SP_ADD>(h, (const double*)h->X, (double*)h->AP, (const double*)h->AP))); }
+    else { DISPATCH_KT(k, (launch_spmm<float, KT, SP_ADD>(h, (const float*)h->X, (float*)h->AP, (const float*)h->AP))); }
   } else {
   if (f64) { DISPATCH_KT(k, (launch_spmm<double, KT, SP_PLAIN>(h, (const double*)h->X, (double*)h->AP, nullptr))); }
   else { DISPATCH_KT(k, (launch_spmm<float, KT, SP_PLAIN>(h, (const float*)h->X, (float*)h->AP, nullptr))); }

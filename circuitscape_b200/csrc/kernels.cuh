@@ -45,6 +45,13 @@ struct PanelCtl {
   unsigned int ticket;    // last-CTA-done counter (self-resetting)
   int init;               // AMG path: 1 while the first z = M^-1 r is being formed
   double rtol, atol;      // stop-test parameters (AMG path reads them on the device)
+  // stagnation guard (reduced-precision storage can plateau above rtol): a column whose
+  // rho has not improved by 10 % for `stall_limit` iterations is frozen; the true-residual
+  // gate then decides, exactly as it does after itmax in the reference (core.jl:639-641)
+  double best[MAXKT];
+  int stall[MAXKT];
+  int stall_limit;
+  int stalled[MAXKT];
 };
 
 // ---------------------------------------------------------------------------
@@ -195,11 +202,16 @@ __device__ __forceinline__ void cg_after_precond(PanelCtl* ctl, const double* rh
       ctl->iters[c] = 0;
       ctl->alpha[c] = 0.0;
       ctl->beta[c] = 0.0;
+      ctl->best[c] = rn;
+      ctl->stall[c] = 0;
+      ctl->stalled[c] = 0;
     } else if (ctl->active[c]) {
       const double ro = ctl->rho[c];
       ctl->beta[c] = ro > 0.0 ? rn / ro : 0.0;
       ctl->rho[c] = rn;
       ctl->iters[c] = it;
+      if (rn < 0.81 * ctl->best[c]) { ctl->best[c] = rn; ctl->stall[c] = 0; }
+      else if (++ctl->stall[c] >= ctl->stall_limit && ctl->stall_limit > 0) { ctl->stalled[c] = 1; ctl->active[c] = 0; }
       if (!(sqrt(rn) > ctl->tol[c]) || it >= ctl->itmax) ctl->active[c] = 0;
     } else {
       ctl->beta[c] = 0.0;
@@ -461,7 +473,8 @@ struct WinMeta {                        // == csb_win::BlockMeta
 
 template <typename T> struct WinCsr {
   const WinMeta* meta;
-  const unsigned char* blob;   // per block: [values | 16-bit local columns | 16-bit row offsets]
+  const unsigned char* blob;   // per block: [values | (1/diag) | 16-bit local columns | 16-bit row offsets]
+  int has_dinv;                // records of square operators carry 1/diag of their rows
   // plain CSR for the direct-gather blocks
   const int* rowptr;
   const int* colidx;
@@ -498,12 +511,14 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
 }
 
 template <typename T, int KT, int MODE, bool WIDE = false> struct WinSmem {
+  // SP_ADD stages the rows of Y it updates through the B slot (ep.B = Y): no synchronous
+  // global load is left in any epilogue
   static constexpr bool NEEDB = (MODE == SP_RESNORM || MODE == SP_RES || MODE == SP_JACOBI ||
-                                 MODE == SP_JACOBI_DOT);
+                                 MODE == SP_JACOBI_DOT || MODE == SP_ADD);
   static constexpr int al(int x) { return (x + 127) / 128 * 128; }
   static constexpr int XW = al((WIDE ? W_WCAP_WIDE : W_WCAP) * KT * (int)sizeof(T));
   static constexpr int BW = NEEDB ? al((W_RB + 8) * KT * (int)sizeof(T)) : 0;
-  static constexpr int VW = al(W_NNZ * ((int)sizeof(T) + 2) + (W_RB + 8) * 2);   // the block's blob
+  static constexpr int VW = al(W_NNZ * ((int)sizeof(T) + 2) + (W_RB + 8) * (2 + (int)sizeof(T)));   // the block's record
   static constexpr int OFF_X = 0;
   static constexpr int OFF_B = OFF_X + XW;
   static constexpr int OFF_V = OFF_B + BW;
@@ -701,7 +716,8 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
         const int roffp = (nrows + 1 + 7) / 8 * 8;
         const int b_lo = row0 & ~3;
         const int b_len = ((row0 + nrows + 3) & ~3) - b_lo;
-        const unsigned blob_bytes = (unsigned)(nnzp * ((int)sizeof(T) + 2) + roffp * 2);
+        const int rowsp = A.has_dinv ? (nrows + 7) / 8 * 8 : 0;
+        const unsigned blob_bytes = (unsigned)(nnzp * ((int)sizeof(T) + 2) + roffp * 2 + rowsp * (int)sizeof(T));
         if (lane == 0) {
           unsigned bytes = (unsigned)(wrows * KT * (int)sizeof(T)) + blob_bytes;
           if (SM::NEEDB) bytes += (unsigned)(b_len * KT * (int)sizeof(T));
@@ -736,7 +752,8 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
         const T* xw = reinterpret_cast<const T*>(base + SM::OFF_X);
         const T* bw = reinterpret_cast<const T*>(base + SM::OFF_B);
         const T* vw = reinterpret_cast<const T*>(base + SM::OFF_V);
-        const unsigned short* lw = reinterpret_cast<const unsigned short*>(vw + nnzp);
+        const T* dw = vw + nnzp;                                  // 1/diag of the block's rows
+        const unsigned short* lw = reinterpret_cast<const unsigned short*>(dw + (A.has_dinv ? (nr + 7) / 8 * 8 : 0));
         const unsigned short* rw = lw + nnzp;
         const int b_lo = row0 & ~3;
         for (int basei = 0; basei < nr; basei += RPP) {
@@ -781,15 +798,14 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
               if (self >= 0) ldvec<T, CPT>(xw + (self + rl) * KT + c0, xo);
               else ldvec<T, CPT>(X + o, xo);
             }
-            if (MODE == SP_ADD) ldvec<T, CPT>(Y + o, out);
             T dv = T(0);
-            if (MODE == SP_JACOBI || MODE == SP_JACOBI_DOT) dv = ep.omega * ep.dinv[row];
+            if (MODE == SP_JACOBI || MODE == SP_JACOBI_DOT) dv = ep.omega * (A.has_dinv ? dw[rl] : ep.dinv[row]);
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
               if (MODE == SP_PLAIN) {
                 out[i] = acc[i];
               } else if (MODE == SP_ADD) {
-                out[i] += acc[i];
+                out[i] = bb[i] + acc[i];
               } else if (MODE == SP_CG) {
                 out[i] = acc[i];
                 dot0[i] += (double)acc[i] * (double)xo[i];
@@ -909,6 +925,7 @@ template <typename T>
 __global__ void k_pack_blob(int nblocks, const WinMeta* __restrict__ meta, const int* __restrict__ perm,
                             const unsigned short* __restrict__ lcol, const unsigned short* __restrict__ roff,
                             const int* __restrict__ roff_off, const T* __restrict__ vals,
+                            const T* __restrict__ dinv /* null: no 1/diag section */,
                             unsigned char* __restrict__ blob) {
   for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
     const WinMeta m = meta[b];
@@ -917,8 +934,11 @@ __global__ void k_pack_blob(int nblocks, const WinMeta* __restrict__ meta, const
     const int roffp = (m.nrows + 1 + 7) / 8 * 8;
     unsigned char* rec = blob + (size_t)m.blob_off16 * 16;
     T* v = reinterpret_cast<T*>(rec);
-    unsigned short* lc = reinterpret_cast<unsigned short*>(v + nnzp);
+    const int rowsp = dinv ? (m.nrows + 7) / 8 * 8 : 0;
+    T* dv = v + nnzp;
+    unsigned short* lc = reinterpret_cast<unsigned short*>(dv + rowsp);
     unsigned short* ro = lc + nnzp;
+    for (int i = threadIdx.x; i < rowsp; i += blockDim.x) dv[i] = i < m.nrows ? dinv[m.row0 + i] : T(0);
     for (int i = threadIdx.x; i < nnzp; i += blockDim.x) {
       const int p = perm[(size_t)m.ent_off + i];
       v[i] = p >= 0 ? vals[p] : T(0);
@@ -973,6 +993,9 @@ k_cg_init(size_t nelem, const T* __restrict__ B, const T* __restrict__ dinv, T* 
       ctl->iters[c] = 0;
       ctl->alpha[c] = 0.0;
       ctl->beta[c] = 0.0;
+      ctl->best[c] = rho;
+      ctl->stall[c] = 0;
+      ctl->stalled[c] = 0;
     }
     __syncthreads();
     if (c == 0) {
@@ -1022,6 +1045,8 @@ k_cg_update_r(size_t nelem, const T* __restrict__ AP, const T* __restrict__ dinv
         ctl->beta[c] = ro > 0.0 ? rn / ro : 0.0;
         ctl->rho[c] = rn;
         ctl->iters[c] = it;
+        if (rn < 0.81 * ctl->best[c]) { ctl->best[c] = rn; ctl->stall[c] = 0; }
+        else if (++ctl->stall[c] >= ctl->stall_limit && ctl->stall_limit > 0) { ctl->stalled[c] = 1; ctl->active[c] = 0; }
         if (!(sqrt(rn) > ctl->tol[c]) || it >= ctl->itmax) ctl->active[c] = 0;
       } else {
         ctl->beta[c] = 0.0;
@@ -1307,13 +1332,16 @@ k_cur_acc(int n, const int* __restrict__ rowptr, const int* __restrict__ colidx,
   }
 }
 
-__global__ void k_set_ctl(PanelCtl* ctl, double rtol, double atol, int itmax) {
+__global__ void k_set_ctl(PanelCtl* ctl, double rtol, double atol, int itmax, int stall_limit) {
+  ctl->stall_limit = stall_limit;
   ctl->rtol = rtol;
   ctl->atol = atol;
   ctl->itmax = itmax;
   ctl->init = 1;
   ctl->iter = 0;
 }
+
+__global__ void k_set_stall(PanelCtl* ctl, int stall_limit) { ctl->stall_limit = stall_limit; }
 
 template <typename T>
 __global__ void k_fill(T* p, size_t n, T v) {

@@ -29,7 +29,7 @@ struct BlockMeta {             // 96 bytes, one per row block (device + host ide
   int nnz;                     // entries of the block
   int ent_off;                 // first entry in vals_p / lcol_p (multiple of 8)
   int blob_off16;              // byte offset / 16 of the block's record in the packed blob:
-                               //   [ values nnzp*sizeof(T) | local cols nnzp*2 | row offsets roffp*2 ]
+                               //   [ values nnzp*sizeof(T) | (1/diag rowsp*sizeof(T)) | local cols nnzp*2 | row offsets roffp*2 ]
   int nseg;                    // 0 => direct-gather path
   int self_slot;               // window slot of X[row0] if rows row0.. are contiguous in it, else -1
   int wrows;                   // total staged X rows
@@ -64,7 +64,8 @@ inline std::vector<int> row_blocks(const int* rowptr, int64_t n) {
 
 inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
                       int64_t ncols_pad /* X rows available (n_pad of the input panel) */,
-                      int vsize = 8 /* sizeof(T) of the device values */, int wcap = WCAP) {
+                      int vsize = 8 /* sizeof(T) of the device values */, int wcap = WCAP,
+                      bool with_dinv = false /* record carries 1/diag of the block's rows */) {
   Windowed w;
   const std::vector<int> bstart = row_blocks(rowptr, nrows);
   const int nb = (int)bstart.size() - 1;
@@ -87,7 +88,8 @@ inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
       const bool fits = cnt <= NNZ_CAP && (r1 - r0) <= RB;
       w.meta[b].blob_off16 = (int)(bo / 16);
       w.roff_off[b] = (int)roff_off[b];
-      if (fits) bo += (int64_t)((cnt + 7) / 8 * 8) * (vsize + 2) + (int64_t)((r1 - r0 + 1 + 7) / 8 * 8) * 2;
+      if (fits) bo += (int64_t)((cnt + 7) / 8 * 8) * (vsize + 2) + (int64_t)((r1 - r0 + 1 + 7) / 8 * 8) * 2 +
+                      (with_dinv ? (int64_t)((r1 - r0 + 7) / 8 * 8) * vsize : 0);
     }
     w.blob_bytes = bo + 64;
   }
