@@ -57,6 +57,7 @@ def factor_from_device(n, nnz, rowptr, colidx, vals, solver, log_transform=False
     f._h = C.c_void_p()
     f.n = n
     f.dtype = np.dtype(np.float64 if vals.dtype == torch.float64 else np.float32)
+    f.io_dtype = f.dtype
     f.solver = solver
     f._keep = (rowptr, colidx, vals)      # the handle borrows these buffers
     opts = _lib.Opts()

@@ -34,7 +34,8 @@ def holey_raster(nr, nc, seed, holes=0.05):
 def test_spmv_matches_scipy(dtype, tol, shape):
     A = holey_raster(*shape, seed=1)
     x = np.random.default_rng(2).standard_normal(A.shape[0])
-    with cb.B200Factor(A, cb.CUDASolver(precision="single" if dtype == np.float32 else "double")) as f:
+    with cb.B200Factor(A, cb.CUDASolver(precision="single" if dtype == np.float32 else "double",
+                                        f32_compute=True)) as f:
         y, _ = f.spmv(x)
     ref = A.astype(dtype) @ x.astype(dtype)
     assert np.abs(y - ref).max() <= tol * np.abs(A).sum(axis=1).max() * np.abs(x).max()
@@ -65,7 +66,7 @@ def test_spmv_window_modes(dtype, tol, window):
     A = holey_raster(123, 77, seed=4, holes=0.15)
     x = np.random.default_rng(2).standard_normal(A.shape[0])
     prec = "single" if dtype == np.float32 else "double"
-    with cb.B200Factor(A, cb.CUDASolver(precision=prec, window=window)) as f:
+    with cb.B200Factor(A, cb.CUDASolver(precision=prec, window=window, f32_compute=True)) as f:
         y, _ = f.spmv(x)
     ref = A.astype(dtype) @ x.astype(dtype)
     assert np.abs(y - ref).max() <= tol * np.abs(A).sum(axis=1).max() * np.abs(x).max()
@@ -114,10 +115,17 @@ def test_pairs_fp32(precond):
     src, dst = graph.all_pairs(nodes)
     Vref = co.solve_pairs_direct(A, src, dst)
     Rref = Vref[dst, np.arange(len(src))]
-    with cb.B200Factor(A, cb.CUDASolver(precision="single", precond=precond)) as f:
+    with cb.B200Factor(A, cb.CUDASolver(precision="single", precond=precond, f32_compute=True)) as f:
         out = f.solve_pairs(src, dst, want_volt=True)
+    assert out["R"].dtype == np.float32
     assert (np.abs(out["R"] - Rref) / Rref).max() < 1e-3
     assert out["relres"].max() < 1e-4
+    # default for precision = single: Float32 at the boundary, fp64 on the device
+    with cb.B200Factor(A.astype(np.float32), cb.CUDASolver(precision="single", precond=precond)) as f:
+        out = f.solve_pairs(src, dst, want_volt=True)
+    assert out["R"].dtype == np.float32 and out["volt"].dtype == np.float32
+    assert (np.abs(out["R"] - Rref) / Rref).max() < 2e-6      # only the fp32 rounding of G and R
+    assert out["relres"].max() < 1e-5
 
 
 def test_amg_cuts_iterations_and_agrees_with_jacobi():
