@@ -79,6 +79,11 @@ struct cs_b200_handle {
   double* d_pinv = nullptr;          // dense pseudo-inverse of the coarsest operator
   double amg_opc = 0.0;              // operator complexity
   bool amg = false;
+  // mixed precision: fp64 CG around an fp32 V-cycle.  lv32 = float copies of every level's
+  // operators and panels (the finest included); R32/X32/T32/Z32 = finest-level float panels.
+  bool mixed = false;
+  std::vector<DevLevel> lv32;
+  void *R32 = nullptr, *X32 = nullptr, *T32 = nullptr, *Z32 = nullptr;
   void *d_cum = nullptr, *d_max = nullptr;
   PanelCtl* d_ctl = nullptr;
   PanelCtl* h_ctl = nullptr;  // pinned
@@ -243,6 +248,48 @@ int build_windowed(cs_b200_handle* h, DevCsr& d, const int* rowptr, const int* c
   return CS_B200_OK;
 }
 
+// Upload a host hierarchy as device levels of type TV.  `own0`: the finest level gets its own
+// device CSR (float copy for the mixed-precision cycle); otherwise it aliases the handle's.
+template <typename TV>
+int upload_levels(cs_b200_handle* h, const csb_amg::Hierarchy& hier, std::vector<DevLevel>& lv, bool own0) {
+  const int nl = (int)hier.levels.size();
+  lv.resize(nl);
+  for (int l = 0; l < nl; ++l) {
+    const csb_amg::HostLevel& hl = hier.levels[l];
+    DevLevel& L = lv[l];
+    L.n = hl.A.nrows;
+    L.n_pad = (L.n + 3) / 4 * 4;
+    L.omega = hl.omega;
+    if (l == 0 && !own0) {
+      L.A = h->A0;  // alias, not owned
+      L.dinv = h->d_dinv;
+    } else {
+      std::vector<TV> dv(L.n_pad, TV(0));
+      for (int64_t i = 0; i < L.n; ++i) dv[i] = (TV)hl.dinv[i];
+      CK(h, cudaMalloc(&L.dinv, (size_t)L.n_pad * sizeof(TV)));
+      CK(h, h2d(h, L.dinv, dv.data(), (size_t)L.n_pad * sizeof(TV)));
+      const bool win = h->opts.window > 0 || (L.n >= 20000 && (win_mask() & (l == 0 ? 1 : 2)));
+      int rc = upload_csr<TV>(h, hl.A, L.A, win, (const TV*)L.dinv);
+      if (rc) return rc;
+      if (l > 0) {
+        const size_t pe = (size_t)L.n_pad * h->ktmax * sizeof(TV);
+        void** bufs[] = {&L.x, &L.b, &L.t, &L.y};
+        for (void** bp : bufs) {
+          CK(h, cudaMalloc(bp, pe));
+          CK(h, cudaMemsetAsync(*bp, 0, pe, h->stream));
+        }
+      }
+    }
+    if (l + 1 < nl) {
+      int rc = upload_csr<TV>(h, hl.P, L.P, L.n >= 20000 && (win_mask() & 4));
+      if (rc) return rc;
+      rc = upload_csr<TV>(h, hl.R, L.R, L.n >= 20000 && (win_mask() & 8));
+      if (rc) return rc;
+    }
+  }
+  return CS_B200_OK;
+}
+
 // Smoothed-aggregation hierarchy: built on the host (amg_host.hpp), resident on the device.
 template <typename T>
 int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<int>& ci,
@@ -255,45 +302,36 @@ int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<i
   csb_amg::Hierarchy hier = csb_amg::build_hierarchy(std::move(a0));
   h->amg_opc = hier.operator_complexity();
   const int nl = (int)hier.levels.size();
-  h->lv.resize(nl);
-  for (int l = 0; l < nl; ++l) {
-    const csb_amg::HostLevel& hl = hier.levels[l];
-    DevLevel& L = h->lv[l];
-    L.n = hl.A.nrows;
-    L.n_pad = (L.n + 3) / 4 * 4;
-    L.omega = hl.omega;
-    if (l == 0) {
-      L.A = h->A0;  // alias, not owned
-      L.dinv = h->d_dinv;
-    } else {
-      std::vector<T> dv(L.n_pad, T(0));
-      for (int64_t i = 0; i < L.n; ++i) dv[i] = (T)hl.dinv[i];
-      CK(h, cudaMalloc(&L.dinv, (size_t)L.n_pad * sizeof(T)));
-      CK(h, h2d(h, L.dinv, dv.data(), (size_t)L.n_pad * sizeof(T)));
-      int rc = upload_csr<T>(h, hl.A, L.A, L.n >= 20000 && (win_mask() & 2), (const T*)L.dinv);
-      if (rc) return rc;
-      const size_t pe = (size_t)L.n_pad * h->ktmax * sizeof(T);
-      void** bufs[] = {&L.x, &L.b, &L.t, &L.y};
-      for (void** bp : bufs) {
-        CK(h, cudaMalloc(bp, pe));
-        CK(h, cudaMemsetAsync(*bp, 0, pe, h->stream));
-      }
+  // fp64 handles run the V-cycle in fp32 (opts.mixed: 0 auto = on, -1 off): the preconditioner
+  // only has to be a good approximate inverse, CG's own vectors stay fp64
+  h->mixed = nl > 1 && sizeof(T) == 8 && h->opts.mixed >= 0;
+  int rc = h->mixed ? upload_levels<float>(h, hier, h->lv32, true) : CS_B200_OK;
+  if (rc) return rc;
+  if (h->mixed) {
+    // the fp64 side only needs level 0's omega / dinv (already on the handle)
+    h->lv.resize(nl);
+    for (int l = 0; l < nl; ++l) { h->lv[l].n = hier.levels[l].A.nrows; h->lv[l].omega = hier.levels[l].omega; }
+    h->lv[0].A = h->A0;
+    h->lv[0].dinv = h->d_dinv;
+    const size_t pe = (size_t)h->n_pad * h->ktmax * sizeof(float);
+    void** bufs[] = {&h->R32, &h->X32, &h->T32, &h->Z32};
+    for (void** bp : bufs) {
+      CK(h, cudaMalloc(bp, pe));
+      CK(h, cudaMemsetAsync(*bp, 0, pe, h->stream));
     }
-    if (l + 1 < nl) {
-      int rc = upload_csr<T>(h, hl.P, L.P, L.n >= 20000 && (win_mask() & 4));
-      if (rc) return rc;
-      rc = upload_csr<T>(h, hl.R, L.R, L.n >= 20000 && (win_mask() & 8));
-      if (rc) return rc;
-    }
+  } else {
+    rc = upload_levels<T>(h, hier, h->lv, false);
+    if (rc) return rc;
+    const size_t pe = (size_t)h->n_pad * h->ktmax * sizeof(T);
+    CK(h, cudaMalloc(&h->Z, pe));
+    CK(h, cudaMemsetAsync(h->Z, 0, pe, h->stream));
   }
   const size_t nc = (size_t)hier.levels.back().A.nrows;
   if (hier.coarse_pinv.size() == nc * nc && nc > 0) {
     CK(h, cudaMalloc(&h->d_pinv, nc * nc * sizeof(double)));
     CK(h, h2d(h, h->d_pinv, hier.coarse_pinv.data(), nc * nc * sizeof(double)));
   }
-  const size_t pe = (size_t)h->n_pad * h->ktmax * sizeof(T);
-  CK(h, cudaMalloc(&h->Z, pe));
-  CK(h, cudaMemsetAsync(h->Z, 0, pe, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
   h->amg = nl > 1;
   return CS_B200_OK;
 }
@@ -479,15 +517,17 @@ int ew_grid_n(cs_b200_handle* h, int64_t n_pad) {
 //   in : h->R (residual, read-only)      out: h->Z ; rho_new = r.z folded into the last kernel
 // Level buffers: b = right-hand side, x = running correction, t = residual scratch,
 // y = post-smoothed correction.  Finest level: b = R, x = stage, t = AP, y = Z.
+struct VcBufs { void *b0, *x0, *t0, *y0; };   // finest-level panels of the cycle
+
 template <typename T, int KT>
-void launch_vcycle(cs_b200_handle* h, bool level0_presmoothed) {
-  const int nl = (int)h->lv.size();
-  auto B = [&](int l) { return l == 0 ? (T*)h->R : (T*)h->lv[l].b; };
-  auto X = [&](int l) { return l == 0 ? (T*)h->stage : (T*)h->lv[l].x; };
-  auto Tm = [&](int l) { return l == 0 ? (T*)h->AP : (T*)h->lv[l].t; };
-  auto Y = [&](int l) { return l == 0 ? (T*)h->Z : (T*)h->lv[l].y; };
+void launch_vcycle_on(cs_b200_handle* h, std::vector<DevLevel>& lv, const VcBufs& vb, bool level0_presmoothed) {
+  const int nl = (int)lv.size();
+  auto B = [&](int l) { return l == 0 ? (T*)vb.b0 : (T*)lv[l].b; };
+  auto X = [&](int l) { return l == 0 ? (T*)vb.x0 : (T*)lv[l].x; };
+  auto Tm = [&](int l) { return l == 0 ? (T*)vb.t0 : (T*)lv[l].t; };
+  auto Y = [&](int l) { return l == 0 ? (T*)vb.y0 : (T*)lv[l].y; };
   for (int l = 0; l < nl - 1; ++l) {
-    DevLevel& L = h->lv[l];
+    DevLevel& L = lv[l];
     const size_t nelem = (size_t)L.n_pad * KT;
     if (!(l == 0 && level0_presmoothed)) {
       k_jacobi0<T, KT><<<ew_grid_n<T, KT>(h, L.n_pad), NT, 0, h->stream>>>(
@@ -498,7 +538,7 @@ void launch_vcycle(cs_b200_handle* h, bool level0_presmoothed) {
     launch_spmm_on<T, KT, SP_PLAIN>(h, L.R, Tm(l), B(l + 1), nullptr, nullptr, 0.0, false);
   }
   {
-    DevLevel& C = h->lv[nl - 1];
+    DevLevel& C = lv[nl - 1];
     if (h->d_pinv) {
       k_coarse_dense<T, KT><<<1, NT, 0, h->stream>>>((int)C.n, h->d_pinv, (const T*)B(nl - 1), Y(nl - 1));
       h->stats.kernel_launches++;
@@ -513,12 +553,24 @@ void launch_vcycle(cs_b200_handle* h, bool level0_presmoothed) {
     }
   }
   for (int l = nl - 2; l >= 0; --l) {
-    DevLevel& L = h->lv[l];
+    DevLevel& L = lv[l];
     launch_spmm_on<T, KT, SP_ADD>(h, L.P, Y(l + 1), X(l), X(l) /* staged as B */, nullptr, 0.0, false);
     if (l == 0)
       launch_spmm_on<T, KT, SP_JACOBI_DOT>(h, L.A, X(l), Y(l), B(l), (const T*)L.dinv, L.omega, true);
     else
       launch_spmm_on<T, KT, SP_JACOBI>(h, L.A, X(l), Y(l), B(l), (const T*)L.dinv, L.omega, false);
+  }
+}
+
+// the cycle of this handle: fp32 copies when `mixed`, else the handle's own type
+template <typename T, int KT>
+void launch_vcycle(cs_b200_handle* h, bool level0_presmoothed) {
+  if (h->mixed) {
+    const VcBufs vb{h->R32, h->X32, h->T32, h->Z32};
+    launch_vcycle_on<float, KT>(h, h->lv32, vb, level0_presmoothed);
+  } else {
+    const VcBufs vb{h->R, h->stage, h->AP, h->Z};
+    launch_vcycle_on<T, KT>(h, h->lv, vb, level0_presmoothed);
   }
 }
 
@@ -536,10 +588,20 @@ void launch_iteration(cs_b200_handle* h) {
   } else {
     // r -= alpha Ap with the finest pre-smoothing folded in; V-cycle; then the deferred
     // x += alpha p together with p = z + beta p  (9 instead of 11 panel passes)
-    k_cg_update_r0<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->AP, (const T*)h->d_dinv,
-                                                   (T)h->lv[0].omega, (T*)h->R, (T*)h->stage, h->d_ctl);
-    launch_vcycle<T, KT>(h, true);
-    k_cg_update_xp2<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->X, (T*)h->P, h->d_ctl);
+    if (h->mixed) {
+      k_cg_update_r0<T, KT, float><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->AP, (const T*)h->d_dinv,
+                                                            (T)h->lv[0].omega, (T*)h->R, (float*)h->X32,
+                                                            (float*)h->R32, h->d_ctl);
+      launch_vcycle<T, KT>(h, true);
+      k_cg_update_xp2<T, KT, float><<<g, NT, 0, h->stream>>>(nelem, (const float*)h->Z32, (T*)h->X, (T*)h->P,
+                                                             h->d_ctl);
+    } else {
+      k_cg_update_r0<T, KT, T><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->AP, (const T*)h->d_dinv,
+                                                        (T)h->lv[0].omega, (T*)h->R, (T*)h->stage, nullptr,
+                                                        h->d_ctl);
+      launch_vcycle<T, KT>(h, true);
+      k_cg_update_xp2<T, KT, T><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->X, (T*)h->P, h->d_ctl);
+    }
     h->stats.kernel_launches += 2;
   }
 }
@@ -600,8 +662,16 @@ int solve_panel(cs_b200_handle* h, double rtol, int64_t itmax) {
     CK(h, cudaMemsetAsync(h->P, 0, nelem * sizeof(T), h->stream));
     CK(h, cudaMemcpyAsync(h->R, h->B, nelem * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
     k_set_ctl<<<1, 1, 0, h->stream>>>(h->d_ctl, rtol, atol, imax, 40);
-    launch_vcycle<T, KT>(h, false);
-    k_cg_update_xp2<T, KT><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->X, (T*)h->P, h->d_ctl);
+    if (h->mixed) {
+      k_convert<T, float><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->R, (float*)h->R32);
+      launch_vcycle<T, KT>(h, false);
+      k_cg_update_xp2<T, KT, float><<<g, NT, 0, h->stream>>>(nelem, (const float*)h->Z32, (T*)h->X, (T*)h->P,
+                                                             h->d_ctl);
+      h->stats.kernel_launches++;
+    } else {
+      launch_vcycle<T, KT>(h, false);
+      k_cg_update_xp2<T, KT, T><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->X, (T*)h->P, h->d_ctl);
+    }
     h->stats.kernel_launches += 2;
   }
   CK(h, cudaGetLastError());
@@ -941,6 +1011,14 @@ void cs_b200_destroy(cs_b200_handle* h) {
     free_csr(L.P);
     free_csr(L.R);
   }
+  for (size_t l = 0; l < h->lv32.size(); ++l) {
+    DevLevel& L = h->lv32[l];
+    free_csr(L.A);
+    cudaFree(L.dinv); cudaFree(L.x); cudaFree(L.b); cudaFree(L.t); cudaFree(L.y);
+    free_csr(L.P);
+    free_csr(L.R);
+  }
+  cudaFree(h->R32); cudaFree(h->X32); cudaFree(h->T32); cudaFree(h->Z32);
   cudaFree(h->Z);
   cudaFree(h->d_pinv);
   void* bufs[] = {h->d_dinv, h->d_bstart, h->X, h->R, h->P, h->AP, h->B, h->stage,

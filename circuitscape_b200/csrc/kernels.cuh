@@ -1093,11 +1093,13 @@ k_cg_update_xp(size_t nelem, const T* __restrict__ R, const T* __restrict__ dinv
 }
 
 // AMG-PCG, after the SpMM:  R -= alpha*AP ;  X0 = omega * Dinv * R   (the zero-guess
-// pre-smoothing sweep of the finest level is folded in: one pass fewer over R)
-template <typename T, int KT>
+// pre-smoothing sweep of the finest level is folded in: one pass fewer over R).
+// TV = type of the V-cycle panels: with TV = float (mixed precision) the kernel also
+// writes the rounded residual R32 the fp32 cycle starts from.
+template <typename T, int KT, typename TV>
 __global__ void __launch_bounds__(NT)
 k_cg_update_r0(size_t nelem, const T* __restrict__ AP, const T* __restrict__ dinv, T omega,
-               T* __restrict__ R, T* __restrict__ X0, const PanelCtl* ctl) {
+               T* __restrict__ R, TV* __restrict__ X0, TV* __restrict__ R32, const PanelCtl* ctl) {
   constexpr int VEC = Vec<T>::N;
   constexpr int L = Log2<KT>::v;
   const size_t e0 = ((size_t)blockIdx.x * NT + threadIdx.x) * VEC;
@@ -1106,23 +1108,26 @@ k_cg_update_r0(size_t nelem, const T* __restrict__ AP, const T* __restrict__ din
 #pragma unroll
   for (int i = 0; i < VEC; ++i) al[i] = (T)ctl->alpha[(e0 + i) % KT];
   for (size_t e = e0; e < nelem; e += stride) {
-    T ap[VEC], r[VEC], x0[VEC];
+    T ap[VEC], r[VEC];
+    TV x0[VEC], r32[VEC];
     vload(AP + e, ap);
     vload(R + e, r);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       r[i] -= al[i] * ap[i];
-      x0[i] = omega * dinv[(e + i) >> L] * r[i];
+      x0[i] = (TV)(omega * dinv[(e + i) >> L] * r[i]);
+      r32[i] = (TV)r[i];
     }
     vstore(R + e, r);
-    vstore(X0 + e, x0);
+    stvec<TV, VEC>(X0 + e, x0);
+    if (R32) stvec<TV, VEC>(R32 + e, r32);
   }
 }
 
 // AMG-PCG, after the V-cycle:  X += alpha*P (the deferred solution update) ;  P = Z + beta*P
-template <typename T, int KT>
+template <typename T, int KT, typename TV>
 __global__ void __launch_bounds__(NT)
-k_cg_update_xp2(size_t nelem, const T* __restrict__ Z, T* __restrict__ X, T* __restrict__ P,
+k_cg_update_xp2(size_t nelem, const TV* __restrict__ Z, T* __restrict__ X, T* __restrict__ P,
                 const PanelCtl* ctl) {
   constexpr int VEC = Vec<T>::N;
   const size_t e0 = ((size_t)blockIdx.x * NT + threadIdx.x) * VEC;
@@ -1134,18 +1139,27 @@ k_cg_update_xp2(size_t nelem, const T* __restrict__ Z, T* __restrict__ X, T* __r
     be[i] = (T)ctl->beta[(e0 + i) % KT];
   }
   for (size_t e = e0; e < nelem; e += stride) {
-    T z[VEC], p[VEC], x[VEC];
-    vload(Z + e, z);
+    TV z[VEC];
+    T p[VEC], x[VEC];
+    ldvec<TV, VEC>(Z + e, z);
     vload(P + e, p);
     vload(X + e, x);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       x[i] += al[i] * p[i];
-      p[i] = z[i] + be[i] * p[i];
+      p[i] = (T)z[i] + be[i] * p[i];
     }
     vstore(X + e, x);
     vstore(P + e, p);
   }
+}
+
+// panel conversion (mixed-precision start-up: R32 = (float) R)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(NT)
+k_convert(size_t nelem, const TI* __restrict__ in, TO* __restrict__ out) {
+  for (size_t e = (size_t)blockIdx.x * NT + threadIdx.x; e < nelem; e += (size_t)gridDim.x * NT)
+    out[e] = (TO)in[e];
 }
 
 // first (zero-guess) damped-Jacobi sweep of a level:  X = omega * Dinv * B

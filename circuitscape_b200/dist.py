@@ -67,6 +67,7 @@ def factor_from_device(n, nnz, rowptr, colidx, vals, solver, log_transform=False
     opts.use_graph = 1 if solver.use_graph else -1
     opts.log_transform = 1 if log_transform else 0
     opts.window = {"auto": 0, "on": 1, "off": -1}[solver.window]
+    opts.mixed = 0 if solver.mixed else -1
     torch.cuda.synchronize()   # the broadcast ran on torch's streams; the library uses its own
     rc = lib.cs_b200_create_from_device(n, nnz, C.c_void_p(rowptr.data_ptr()), C.c_void_p(colidx.data_ptr()),
                                         C.c_void_p(vals.data_ptr()), _lib.dtype_code(f.dtype),

@@ -41,6 +41,7 @@ class CUDASolver:
     use_graph: bool = True
     window: str = "auto"             # TMA-staged windowed SpMM: auto | on | off
     f32_compute: bool = False        # precision = single: keep fp32 ON THE DEVICE too (see B200Factor)
+    mixed: bool = True               # fp64 + AMG: fp32 V-cycle inside fp64 CG
 
     @property
     def dtype(self):
@@ -91,6 +92,7 @@ class B200Factor:
         opts.use_graph = 1 if solver.use_graph else -1
         opts.log_transform = 1 if log_transform else 0
         opts.window = {"auto": 0, "on": 1, "off": -1}[solver.window]
+        opts.mixed = 0 if solver.mixed else -1
         rc = lib.cs_b200_create(self.n, m.nnz, _lib._ptr(rowptr), _lib._ptr(colidx), _lib._ptr(vals),
                                 bits, 0, _lib.dtype_code(self.dtype), solver.device,
                                 C.byref(opts), C.byref(self._h))

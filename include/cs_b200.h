@@ -69,7 +69,10 @@ typedef struct cs_b200_opts {
   int32_t log_transform;  /* current maps accumulate log10(c) (src/out.jl:305-309)  */
   int32_t window;         /* TMA-staged windowed SpMM: 0 auto (operators >= 20000 rows),
                              1 always, -1 never (plain direct-gather kernel)         */
-  int32_t reserved[6];
+  int32_t mixed;          /* fp64 handles with AMG: run the V-cycle in fp32 (CG vectors,
+                             dot products and the residual gate stay fp64): 0 auto (on),
+                             -1 off                                                  */
+  int32_t reserved[5];
 } cs_b200_opts;
 
 /* Per-call statistics (milliseconds measured with CUDA events on the solve stream). */

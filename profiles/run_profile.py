@@ -19,12 +19,13 @@ ap.add_argument("--rows", type=int, default=3163)
 ap.add_argument("--what", default="spmm", choices=["spmm", "cg", "solve"])
 ap.add_argument("--precision", default="double")
 ap.add_argument("--precond", default="jacobi")
+ap.add_argument("--no-mixed", action="store_true")
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 L, _ = graph.synthetic_raster_laplacian(a.rows, a.rows, seed=42)
 n, nnz = L.shape[0], L.nnz
 sv = 8 if a.precision == "double" else 4
-with cb.construct_cholesky_factor(L, cb.CUDASolver(precision=a.precision, precond=a.precond)) as f:
+with cb.construct_cholesky_factor(L, cb.CUDASolver(precision=a.precision, precond=a.precond, mixed=not a.no_mixed)) as f:
     if a.what == "spmm":
         for k in (1, 8):
             ms = f.bench_spmm(k, reps=a.reps, flush_l2=True)

@@ -143,6 +143,25 @@ def test_amg_cuts_iterations_and_agrees_with_jacobi():
     assert np.array_equal(oa["R"], oa2["R"]), "AMG path must be bit-reproducible"
 
 
+def test_mixed_precision_cycle_matches_fp64_cycle():
+    """fp32 V-cycle inside fp64 CG (default) vs the all-fp64 cycle: same answers to the
+    solver tolerance, comparable iteration counts, fp64-level residual gate."""
+    A = holey_raster(220, 160, seed=31)
+    nodes = graph.focal_nodes(A.shape[0], 5, seed=3)
+    src, dst = graph.all_pairs(nodes)
+    Vref = co.solve_pairs_direct(A, src, dst)
+    Rref = Vref[dst, np.arange(len(src))]
+    res = {}
+    for mixed in (True, False):
+        with cb.B200Factor(A, cb.CUDASolver(precond="amg", mixed=mixed, window="on")) as f:
+            res[mixed] = f.solve_pairs(src, dst, want_volt=True)
+    for mixed, o in res.items():
+        assert (np.abs(o["R"] - Rref) / Rref).max() < 1e-6, mixed
+        assert (np.abs(o["volt"] - Vref).max(axis=0) / Rref).max() < 1e-5, mixed
+        assert o["relres"].max() < 1e-5, mixed
+    assert res[True]["iters"].max() <= res[False]["iters"].max() + 4
+
+
 def test_amg_irregular_graph_with_hub():
     """network-style graph (config 5 shape): power-law-ish degrees incl. a hub row
     longer than one shared-memory row block, advanced-mode SPD system."""
