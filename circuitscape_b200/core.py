@@ -439,3 +439,157 @@ def advanced_kernel(prob: AdvancedProblem, flags: Flags, cfg=None) -> AdvancedOu
         res.node_currents = node_currents_host(G, voltages, prob.finitegrounds)
         res.branch = _branch_currents(G, voltages, np.arange(1, n + 1))
     return res
+
+
+# ---------------------------------------------------------------------------
+# one-to-all / all-to-one  (src/raster/onetoall.jl) -- callers of the advanced kernel
+# ---------------------------------------------------------------------------
+def resolve_conflicts(sources, grounds, policy):
+    """src/raster/advanced.jl:119-149 (`rmvall` only zeroes the sources -- pinned upstream by
+    test/internal.jl:130-135)."""
+    sources = np.array(sources, dtype=np.float64)
+    grounds = np.array(grounds, dtype=np.float64)
+    finite = np.where(np.isfinite(grounds), grounds, 0.0)
+    if not np.any(finite != 0):
+        finite = np.array([NODATA])
+    both = (sources != 0) & (grounds != 0)
+    if policy in ("rmvsrc", "rmvall"):
+        sources[both] = 0
+    elif policy == "rmvgnd":
+        grounds[both] = 0
+    grounds[np.isinf(grounds) & (sources > 0)] = 0
+    return sources, grounds, finite
+
+
+def sources_and_grounds_from_maps(source_map, ground_map, nodemap, n, policy):
+    """src/raster/advanced.jl:81-117 (raster branch): cell values accumulate on their node."""
+    sources = np.zeros(n)
+    grounds = np.zeros(n)
+    for target, cmap in ((sources, source_map), (grounds, ground_map)):
+        sel = (cmap != 0) & (nodemap != 0)
+        np.add.at(target, nodemap[sel] - 1, cmap[sel])
+    return resolve_conflicts(sources, grounds, policy)
+
+
+@dataclass
+class RasterData:
+    """The fields of src/io.jl:34-43 the one-to-all driver reads."""
+    cellmap: np.ndarray
+    polymap: np.ndarray | None
+    points_rc: tuple                 # (rows, cols, ids) 1-based, sorted by id
+    strengths: np.ndarray | None = None       # (P, 2) id, strength
+    included_pairs: object | None = None      # .mode, .point_ids, .mat
+
+
+@dataclass
+class OneToAllOutput:
+    resistances: np.ndarray
+    curmaps: dict = field(default_factory=dict)
+    voltmaps: dict = field(default_factory=dict)
+    cum_curmap: np.ndarray | None = None
+    max_curmap: np.ndarray | None = None
+    num_solves: int = 0
+
+
+def onetoall_kernel(data: RasterData, flags: Flags, cfg, solver=None, one_to_all=None,
+                    four_neighbors=False, avg_res=False) -> OneToAllOutput:
+    """src/raster/onetoall.jl:13-167.  One advanced-mode solve per focal id: one-to-all = unit
+    (or variable-strength) source at the focal node, every other focal node a direct ground;
+    all-to-one = the reverse.  Every solve goes through `multiple_solver` -> hook #3."""
+    from . import graph
+    solver = solver or get_solver(cfg)
+    if one_to_all is None:
+        one_to_all = cfg.get("scenario") in ("one-to-all", "one_to_all")
+    o = flags.outputflags
+    gmap, polymap = data.cellmap, data.polymap
+    rr, cc_, ids = (np.asarray(a) for a in data.points_rc)
+    strengths = None if data.strengths is None else np.array(data.strengths, dtype=np.float64)
+    inc = data.included_pairs
+    mode = 0 if (inc is not None and inc.mode == "include") else 1
+    if inc is not None:
+        keep = np.isin(ids, inc.point_ids)
+        rr, cc_, ids = rr[keep], cc_[keep], ids[keep]
+        if strengths is not None:
+            strengths = strengths[np.isin(strengths[:, 0], inc.point_ids)]
+    points_rc = (rr, cc_, ids)
+    point_map = np.zeros(gmap.shape, dtype=np.int64)
+    point_map[rr - 1, cc_ - 1] = ids
+    uniq = list(dict.fromkeys(int(p) for p in ids))
+    newpoly = graph.create_new_polymap(gmap, polymap, points_rc, point_map)
+    nodemap = graph.construct_node_map(gmap, newpoly)
+    adj = graph.construct_graph(gmap, nodemap, avg_res, four_neighbors)
+    comps = graph.connected_components(adj)
+    G = graph.laplacian(adj)
+    first = {p: int(np.nonzero(ids == p)[0][0]) for p in uniq}
+    unique_point_map = np.zeros(gmap.shape, dtype=np.int64)
+    for p, k in first.items():
+        unique_point_map[rr[k] - 1, cc_[k] - 1] = p
+    out = OneToAllOutput(resistances=None)
+    out.cum_curmap = np.zeros(gmap.shape)
+    out.max_curmap = np.full(gmap.shape, NODATA) if o.write_max_cur_maps else None
+    res = np.zeros(len(uniq))
+    strength_map = np.zeros(gmap.shape) if strengths is not None else None
+    for i, n in enumerate(uniq):
+        pm, nm, npoly = point_map.copy(), nodemap, newpoly
+        if inc is not None:
+            for j, other in enumerate(inc.point_ids):
+                if i != j and inc.mat[i, j] == mode:
+                    pm[pm == int(other)] = 0
+            npoly = graph.create_new_polymap(gmap, polymap, points_rc, pm)
+            nm = graph.construct_node_map(gmap, polymap)            # (sic) onetoall.jl:88
+        if strengths is not None:
+            st = strengths.copy()
+            st[pm[rr - 1, cc_ - 1] == 0, 1] = 1
+            strength_map[rr - 1, cc_ - 1] = st[:, 1]
+        if pm.sum() == n:                                           # no other focal node left
+            res[i] = -1
+            continue
+        if one_to_all:
+            strv = strengths[i, 1] if strengths is not None else 1.0
+            source_map = np.where(unique_point_map == n, float(strv), 0.0)
+            ground_map = np.where((pm != n) & (pm > 0), np.inf, 0.0)
+            policy = "rmvgnd"
+        else:
+            if strengths is not None:
+                source_map = np.where(unique_point_map == n, 0.0, strength_map)
+            else:
+                source_map = np.where((unique_point_map != 0) & (pm != n), 1.0, 0.0)
+            ground_map = np.where(pm == n, np.inf, 0.0)
+            policy = "rmvsrc"
+        check_node = nm[rr[i] - 1, cc_[i] - 1]                      # (sic) row i of points_rc
+        s_, g_, f_ = sources_and_grounds_from_maps(source_map, ground_map, nm, G.shape[0], policy)
+        volt = np.zeros(gmap.shape)
+        outvolt, outcurr, called = np.zeros(gmap.shape), np.zeros(gmap.shape), False
+        for comp in comps:
+            if check_node not in comp:                               # advanced.jl:186-188
+                continue
+            rows = np.asarray(comp) - 1
+            sl, gl = s_[rows].copy(), g_[rows].copy()
+            if sl.sum() == 0 or gl.sum() == 0:
+                continue
+            fl = f_[rows] if f_[0] != NODATA else f_
+            a_local = G[rows][:, rows].tocsr()
+            v = multiple_solver(cfg, solver, a_local, sl, gl, fl)
+            out.num_solves += 1
+            lm = construct_local_node_map(nm, np.asarray(comp), npoly)
+            called = True
+            outvolt += _scatter(v, lm)
+            outcurr += _scatter(node_currents_host(a_local, v, fl), lm)
+            volt[lm != 0] = v[lm[lm != 0] - 1]
+        if not called:
+            res[i] = -1                                              # advanced.jl:246-250
+        elif one_to_all:
+            val = volt[source_map != 0] / source_map[source_map != 0]
+            res[i] = -1 if np.isclose(val[0], 0) else val[0]         # advanced.jl:252-263
+        else:
+            res[i] = 0
+        if o.write_volt_maps:
+            out.voltmaps[n] = outvolt
+        if o.write_cur_maps or o.write_cum_cur_map_only:
+            out.curmaps[n] = outcurr
+        out.cum_curmap += outcurr
+        if out.max_curmap is not None:
+            out.max_curmap = np.maximum(out.max_curmap, outcurr)
+    out.resistances = np.column_stack([uniq, res])
+    out.cum_curmap = np.where(out.cum_curmap < NODATA, NODATA, out.cum_curmap)
+    return out

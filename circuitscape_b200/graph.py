@@ -38,6 +38,32 @@ def construct_node_map(gmap, polymap=None):
     return lab.reshape(g.shape, order="F")
 
 
+def create_new_polymap(gmap, polymap, points_rc, point_map):
+    """Merge focal points into the short-circuit polygon map (one-to-all / all-to-one,
+    src/raster/pairwise.jl:374-403): a focal id becomes a polygon of its own unless it
+    already sits on one; focal *regions* overlapping a polygon take it over."""
+    rr, cc, ids = points_rc
+    if polymap is None or np.size(polymap) == 0:
+        return np.array(point_map, dtype=np.int64)
+    newpoly = np.array(polymap, dtype=np.int64)
+    occupied = np.flatnonzero(np.asarray(point_map).reshape(-1, order="F"))
+    cells = np.column_stack(np.unravel_index(occupied, point_map.shape, order="F"))
+    if len(ids) == len(np.unique(ids)):
+        k = int(np.max(polymap))
+        for a, b in cells:
+            if polymap[a, b] == 0:
+                newpoly[a, b] = point_map[a, b] + k
+        return newpoly
+    k = max(int(np.max(polymap)), int(np.max(point_map)))
+    for a, b in cells:
+        v1, v2 = int(point_map[a, b]), int(newpoly[a, b])
+        if v2 == 0:
+            newpoly[a, b] = k + v1
+        elif v1 != v2:
+            newpoly[newpoly == v2] = v1
+    return newpoly
+
+
 def construct_graph(gmap, nodemap, avg_res, four_neighbors):
     """Symmetric adjacency of conductances: E, S, SE, NE neighbours, duplicates
     (parallel cell adjacencies of merged nodes) summed."""

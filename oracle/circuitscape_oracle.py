@@ -986,6 +986,153 @@ def network_advanced(cfg, inputs, solver="direct"):
 
 
 # ----------------------------------------------------------------------------
+# one-to-all / all-to-one (raster/onetoall.jl) -- callers of the advanced kernel
+# ----------------------------------------------------------------------------
+def create_new_polymap_pointmap(gmap, polymap, points_rc, point_map):
+    """raster/pairwise.jl:374-403 (the branch with a non-empty point_map)."""
+    if polymap is None or np.size(polymap) == 0:
+        return point_map.copy()
+    newpoly = polymap.copy()
+    no_polys = len(points_rc[2]) == len(np.unique(points_rc[2]))
+    r, c = colmajor_nonzero(point_map != 0)
+    if no_polys:
+        k = polymap.max()
+        for a, b in zip(r, c):
+            if polymap[a, b] == 0:
+                newpoly[a, b] = point_map[a, b] + k
+    else:
+        k = max(polymap.max(), point_map.max())
+        for a, b in zip(r, c):
+            v1, v2 = point_map[a, b], newpoly[a, b]
+            if v2 == 0:
+                newpoly[a, b] = k + v1
+            elif v1 != v2:
+                newpoly[newpoly == v2] = v1
+    return newpoly
+
+
+@dataclass
+class OneToAllResult:
+    resistances: np.ndarray                    # (P, 2): id, value  (raster/onetoall.jl:166)
+    curmaps: dict = field(default_factory=dict)
+    voltmaps: dict = field(default_factory=dict)
+    cum_curmap: np.ndarray | None = None
+    max_curmap: np.ndarray | None = None
+
+
+def raster_one_to_all(cfg, inputs, solver="direct"):
+    """raster/onetoall.jl:1-167; scenario one-to-all or all-to-one from cfg."""
+    flags = cfg_flags(cfg)
+    one_to_all = cfg.get("scenario") in ("one-to-all", "one_to_all")
+    cellmap, polymap, meta, inc = load_raster_inputs(cfg, inputs)
+    pk = inputs["point_file"]
+    points_rc = read_point_map(pk[0], pk[1], meta)
+    strengths = None
+    if cfg_bool(cfg, "use_variable_source_strengths"):
+        strengths = np.asarray(inputs["variable_source_file"][1], dtype=np.float64).reshape(-1, 2).copy()   # io.jl:84-89
+        if strengths[:, 0].min() == 0:
+            strengths[:, 0] += 1
+    use_inc = inc is not None
+    mode = 0 if (use_inc and inc.mode == "include") else 1
+    if use_inc:
+        keep = np.isin(points_rc[2], inc.point_ids)                   # prune_points!
+        points_rc = tuple(a[keep] for a in points_rc)
+        if strengths is not None:                                     # prune_strengths
+            strengths = strengths[np.isin(strengths[:, 0], inc.point_ids)]
+    rr, cc_, ids = points_rc
+    point_map = np.zeros(cellmap.shape, dtype=np.int64)
+    point_map[rr - 1, cc_ - 1] = ids
+    points_unique = list(dict.fromkeys(int(p) for p in ids))
+    newpoly = create_new_polymap_pointmap(cellmap, polymap, points_rc, point_map)
+    nodemap = construct_node_map(cellmap, newpoly)
+    a = construct_graph(cellmap, nodemap, flags["avg_res"], flags["four_neighbors"])
+    cc = connected_components(a)
+    G = laplacian(a)
+    n_nodes = G.shape[0]
+    unique_point_map = np.zeros(cellmap.shape, dtype=np.int64)
+    for p in points_unique:
+        ind = int(np.nonzero(ids == p)[0][0])
+        unique_point_map[rr[ind] - 1, cc_[ind] - 1] = ids[ind]
+    res = np.zeros(len(points_unique))
+    out = OneToAllResult(resistances=None)
+    out.cum_curmap = np.zeros(cellmap.shape)
+    out.max_curmap = np.full(cellmap.shape, NODATA) if flags["write_max_cur_maps"] else None
+    strength_map = np.zeros(cellmap.shape) if strengths is not None else None
+    for i, n in enumerate(points_unique):
+        pm = point_map.copy()
+        nm, npoly = nodemap, newpoly
+        strv = strengths[i, 1] if strengths is not None else 1.0
+        if use_inc:
+            for j in range(len(inc.point_ids)):
+                if i != j and inc.mat[i, j] == mode:
+                    pm[pm == int(inc.point_ids[j])] = 0
+            npoly = create_new_polymap_pointmap(cellmap, polymap, points_rc, pm)
+            nm = construct_node_map(cellmap, polymap)                 # (sic) raster/onetoall.jl:88
+        if strengths is not None:
+            tmp = pm[rr - 1, cc_ - 1]
+            st2 = strengths.copy()
+            st2[tmp == 0, 1] = 1
+            strength_map[rr - 1, cc_ - 1] = st2[:, 1]
+        if pm.sum() == n:
+            res[i] = -1
+            continue
+        if one_to_all:
+            source_map = np.where(unique_point_map == n, float(strv), 0.0)
+            ground_map = np.where(pm == n, 0.0, pm.astype(np.float64))
+            ground_map = np.where(ground_map > 0, np.inf, ground_map)
+            policy = "rmvgnd"
+        else:
+            if strengths is not None:
+                source_map = np.where(unique_point_map == n, 0.0, strength_map)
+            else:
+                source_map = np.where(unique_point_map != 0, 1.0, 0.0)
+                source_map = np.where(pm == n, 0.0, source_map)
+            ground_map = np.where(pm == n, np.inf, 0.0)
+            policy = "rmvsrc"
+        check_node = nm[rr[i] - 1, cc_[i] - 1]                        # (sic) indexes points_rc by i
+        s_, g_, f_ = _sources_grounds_raster(source_map, ground_map, nm, n_nodes, policy)
+        # advanced_kernel restricted to the component of check_node (raster/advanced.jl:186-188)
+        volt = np.zeros(cellmap.shape)
+        outvolt = np.zeros(cellmap.shape)
+        outcurr = np.zeros(cellmap.shape)
+        called = False
+        Gc = sp.csr_matrix(G)
+        for comp in cc:
+            if check_node not in comp:
+                continue
+            idx = np.asarray(comp) - 1
+            sl, gl = s_[idx].copy(), g_[idx].copy()
+            if sl.sum() == 0 or gl.sum() == 0:
+                continue
+            fl = f_[idx] if f_[0] != NODATA else f_
+            a_local = Gc[idx][:, idx].tocsr()
+            v = multiple_solver(a_local, sl, gl, fl, solver)
+            local_nodemap = construct_local_node_map(nm, comp, npoly)
+            called = True
+            outvolt += scatter_to_raster(v, local_nodemap)
+            outcurr += scatter_to_raster(get_node_currents(a_local, v, fl), local_nodemap)
+            lm = local_nodemap
+            volt[lm != 0] = v[lm[lm != 0] - 1]
+        if not called:
+            res[i] = -1
+        elif one_to_all:
+            val = volt[source_map != 0] / source_map[source_map != 0]
+            res[i] = -1 if np.isclose(val[0], 0) else val[0]
+        else:
+            res[i] = 0
+        if flags["write_volt_maps"]:
+            out.voltmaps[n] = outvolt
+        if flags["write_cur_maps"] or flags["write_cum_cur_map_only"]:
+            out.curmaps[n] = outcurr
+        out.cum_curmap += outcurr                                      # raster/onetoall.jl:153-158
+        if out.max_curmap is not None:
+            out.max_curmap = np.maximum(out.max_curmap, outcurr)
+    out.resistances = np.column_stack([points_unique, res])
+    out.cum_curmap = np.where(out.cum_curmap < NODATA, NODATA, out.cum_curmap)
+    return out
+
+
+# ----------------------------------------------------------------------------
 # fixtures helper
 # ----------------------------------------------------------------------------
 def load_case(npz, name):

@@ -190,3 +190,39 @@ def check_advanced(r, exp, flags, map_tol=TOL):
     v = exp["branch_currents.txt"].copy(); v[:, :2] += 1
     assert mine.shape == v.shape
     assert np.sum((sorted_rows(mine) - sorted_rows(v)) ** 2) < map_tol
+
+
+def onetoall_problem(golden, name):
+    """-> (RasterData, flags, cfg, expected) for the one-to-all / all-to-one goldens."""
+    cfg, inp, exp = co.load_case(golden, name)
+    flags = cb.Flags.from_cfg(cfg)
+    cellmap, polymap, meta, inc = co.load_raster_inputs(cfg, inp)
+    pk = inp["point_file"]
+    points_rc = co.read_point_map(pk[0], pk[1], meta)
+    strengths = None
+    if co.cfg_bool(cfg, "use_variable_source_strengths"):
+        strengths = np.asarray(inp["variable_source_file"][1], dtype=np.float64).reshape(-1, 2).copy()
+        if strengths[:, 0].min() == 0:
+            strengths[:, 0] += 1
+    data = cb.RasterData(cellmap, polymap, points_rc, strengths, inc)
+    return data, flags, cfg, exp
+
+
+def check_onetoall(r, exp, flags, map_tol=TOL):
+    x = exp["resistances.out"]
+    assert x.shape == r.resistances.shape
+    assert np.all(np.abs(x - r.resistances) <= np.sqrt(TOL))             # test_utils.jl:125-128
+    assert np.abs(x - r.resistances).max() <= 1e-6 * max(1.0, np.abs(x).max())
+    o = flags.outputflags
+    n = 0
+    for pid, m in r.curmaps.items():                                      # only files the reference writes
+        assert np.sum((m - exp[f"curmap_{pid}.asc"]) ** 2) < map_tol
+        n += 1
+    for pid, m in r.voltmaps.items():
+        assert np.sum((m - exp[f"voltmap_{pid}.asc"]) ** 2) < map_tol
+        n += 1
+    if (o.write_cur_maps or o.write_cum_cur_map_only) and "cum_curmap.asc" in exp:
+        assert np.sum((r.cum_curmap - exp["cum_curmap.asc"]) ** 2) < map_tol
+    if o.write_max_cur_maps and "max_curmap.asc" in exp:
+        assert np.sum((r.max_curmap - exp["max_curmap.asc"]) ** 2) < map_tol
+    return n

@@ -8,7 +8,7 @@ TEST INFRASTRUCTURE.  Run in the BUILD container only (it reads
 
 It parses the INI jobs of the reference's integration suite
 (/root/reference/test/test_utils.jl:77-121: network pairwise 1-3, network
-advanced 1-3, raster pairwise 1-17, raster advanced 1-6), every input file
+advanced 1-3, raster pairwise 1-17, raster advanced 1-6, one-to-all 1-13, all-to-one 1-12), every input file
 each job names, and every expected-output file `test/output_verify/<case>_*`,
 and stores them as arrays in `tests/golden/reference_cases.npz`.
 
@@ -182,6 +182,10 @@ def cases():
         yield f"sgNetworkVerify{i}", f"input/network/sgNetworkVerify{i}.ini"
     for i in range(1, 4):
         yield f"mgNetworkVerify{i}", f"input/network/mgNetworkVerify{i}.ini"
+    for i in range(1, 14):
+        yield f"oneToAllVerify{i}", f"input/raster/one_to_all/{i}/oneToAllVerify{i}.ini"
+    for i in range(1, 13):
+        yield f"allToOneVerify{i}", f"input/raster/all_to_one/{i}/allToOneVerify{i}.ini"
 
 
 def main():

@@ -271,6 +271,16 @@ def test_golden_advanced(golden, name, precond):
     cases.check_advanced(cb.advanced_kernel(prob, flags), exp, flags)
 
 
+@pytest.mark.parametrize("name", [f"oneToAllVerify{i}" for i in (1, 4, 7, 10, 12, 13)] +
+                         [f"allToOneVerify{i}" for i in (1, 4, 7, 12)])
+def test_golden_onetoall(golden, name):
+    data, flags, cfg, exp = cases.onetoall_problem(golden, name)
+    fl = co.cfg_flags(cfg)
+    r = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(rtol=1e-8),
+                           four_neighbors=fl["four_neighbors"], avg_res=fl["avg_res"])
+    cases.check_onetoall(r, exp, flags)
+
+
 def test_golden_default_rtol_meets_reference_bar(golden):
     """with the reference's own rtol = 1e-6 (src/core.jl:639) the reference's own
     tolerances (1e-3 abs on R, sum d^2 < 1e-6 on maps) must hold."""

@@ -7,6 +7,8 @@ import pytest
 import circuitscape_b200 as cb
 from circuitscape_b200 import solver as S
 
+from oracle import circuitscape_oracle as co
+
 from . import cases
 from .fake_factor import FakeFactor
 
@@ -35,6 +37,19 @@ def test_network_pairwise_driver(golden, i):
 def test_advanced_driver(golden, name):
     prob, flags, exp = cases.advanced_problem(golden, name, cb.CUDASolver())
     cases.check_advanced(cb.advanced_kernel(prob, flags), exp, flags)
+
+
+ONE_TO_ALL = [f"oneToAllVerify{i}" for i in range(1, 14)] + [f"allToOneVerify{i}" for i in range(1, 13)]
+
+
+@pytest.mark.parametrize("name", ONE_TO_ALL)
+def test_onetoall_driver(golden, name):
+    """src/raster/onetoall.jl through the advanced kernel (test/test_utils.jl:123-139)."""
+    data, flags, cfg, exp = cases.onetoall_problem(golden, name)
+    fl = co.cfg_flags(cfg)
+    r = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(),
+                           four_neighbors=fl["four_neighbors"], avg_res=fl["avg_res"])
+    cases.check_onetoall(r, exp, flags)
 
 
 def test_batching_is_transparent(golden):

@@ -147,3 +147,24 @@ def test_cg_amg_advanced(golden):
     r = co.raster_advanced(cfg, inp, "cg+amg")
     assert np.sum((r.curmap - exp["curmap.asc"]) ** 2) < TOL
     assert np.sum((r.voltmap - exp["voltmap.asc"]) ** 2) < TOL
+
+
+@pytest.mark.parametrize("name", [f"oneToAllVerify{i}" for i in range(1, 14)] +
+                         [f"allToOneVerify{i}" for i in range(1, 13)])
+def test_one_to_all_and_all_to_one(golden, name):
+    """raster/onetoall.jl restated (next row of the scope table): resistances of every case
+    and every map the current reference writes (test/test_utils.jl:123-139)."""
+    cfg, inp, exp = co.load_case(golden, name)
+    r = co.raster_one_to_all(cfg, inp, "direct")
+    x = exp["resistances.out"]
+    assert x.shape == r.resistances.shape
+    assert np.all(np.abs(x - r.resistances) <= np.sqrt(TOL))
+    fl = co.cfg_flags(cfg)
+    for n, m in r.curmaps.items():
+        assert np.sum((m - exp[f"curmap_{n}.asc"]) ** 2) < TOL
+    for n, m in r.voltmaps.items():
+        assert np.sum((m - exp[f"voltmap_{n}.asc"]) ** 2) < TOL
+    if (fl["write_cur_maps"] or fl["write_cum_cur_map_only"]) and "cum_curmap.asc" in exp:
+        assert np.sum((r.cum_curmap - exp["cum_curmap.asc"]) ** 2) < TOL
+    if fl["write_max_cur_maps"] and "max_curmap.asc" in exp:
+        assert np.sum((r.max_curmap - exp["max_curmap.asc"]) ** 2) < TOL
