@@ -10,7 +10,7 @@
 //   tentative T   piecewise constant, columns normalised (candidate = ones)
 //   prolongator   P = (I - (4/3)/rho * D^-1 A) T,  rho = ||D^-1 A||_inf >= rho(D^-1 A)
 //   coarse op     A_c = P^T A P  (Galerkin)
-//   coarsest      dense symmetric pseudo-inverse (cyclic Jacobi eigen-solver)
+//   coarsest      (<= 200 nodes) dense symmetric pseudo-inverse, cyclic Jacobi eigen-solver
 // The smoother on the device is damped Jacobi with omega = (4/3)/rho_l per level, so
 // the V(1,1) cycle is a symmetric positive (semi-)definite operator as CG requires.
 #pragma once
@@ -223,7 +223,7 @@ inline void diag_and_rho(const Csr& a, std::vector<double>& dinv, double& rho) {
   if (!(rho > 0.0)) rho = 1.0;
 }
 
-inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 96) {
+inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 200) {
   Hierarchy h;
   h.levels.emplace_back();
   h.levels.back().A = std::move(a0);
