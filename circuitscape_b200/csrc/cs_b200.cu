@@ -540,7 +540,7 @@ void launch_vcycle_on(cs_b200_handle* h, std::vector<DevLevel>& lv, const VcBufs
   {
     DevLevel& C = lv[nl - 1];
     if (h->d_pinv) {
-      k_coarse_dense<T, KT><<<1, NT, 0, h->stream>>>((int)C.n, h->d_pinv, (const T*)B(nl - 1), Y(nl - 1));
+      k_coarse_dense<T, KT><<<((int)C.n * KT + NT - 1) / NT, NT, 0, h->stream>>>((int)C.n, h->d_pinv, (const T*)B(nl - 1), Y(nl - 1));
       h->stats.kernel_launches++;
     } else {  // coarsening stalled above the dense limit: 4 damped-Jacobi sweeps (symmetric)
       const int l = nl - 1;

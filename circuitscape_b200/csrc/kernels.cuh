@@ -1179,16 +1179,25 @@ k_jacobi0(size_t nelem, const T* __restrict__ B, const T* __restrict__ dinv, T o
   }
 }
 
-// coarsest level:  X = Pinv * B  (dense n x n pseudo-inverse in double, one CTA)
+// coarsest level:  X = Pinv * B  (dense n x n pseudo-inverse in double).  One thread per
+// output (row, column), 4 independent accumulators; launched over ceil(n*KT/NT) CTAs.
 template <typename T, int KT>
 __global__ void __launch_bounds__(NT)
 k_coarse_dense(int n, const double* __restrict__ pinv, const T* __restrict__ B, T* __restrict__ X) {
-  for (int e = threadIdx.x; e < n * KT; e += NT) {
-    const int i = e / KT, c = e % KT;
-    double acc = 0.0;
-    for (int j = 0; j < n; ++j) acc += pinv[(size_t)i * n + j] * (double)B[(size_t)j * KT + c];
-    X[e] = (T)acc;
+  const int e = blockIdx.x * NT + threadIdx.x;
+  if (e >= n * KT) return;
+  const int i = e / KT, c = e % KT;
+  const double* row = pinv + (size_t)i * n;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int j = 0;
+  for (; j + 3 < n; j += 4) {
+    a0 += row[j] * (double)B[(size_t)j * KT + c];
+    a1 += row[j + 1] * (double)B[(size_t)(j + 1) * KT + c];
+    a2 += row[j + 2] * (double)B[(size_t)(j + 2) * KT + c];
+    a3 += row[j + 3] * (double)B[(size_t)(j + 3) * KT + c];
   }
+  for (; j < n; ++j) a0 += row[j] * (double)B[(size_t)j * KT + c];
+  X[e] = (T)((a0 + a1) + (a2 + a3));
 }
 
 // ---------------------------------------------------------------------------
