@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--precision", default="double")
     ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"])
     ap.add_argument("--rtol", type=float, default=1e-6)
+    ap.add_argument("--loop", default="device", choices=["device", "chunk", "plain"],
+                    help="PCG loop control: device-side WHILE graph | host-polled graph chunks | plain launches")
     ap.add_argument("--skip-spmv1e7", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU sample (0 = #cores)")
@@ -239,7 +241,8 @@ def main():
         dist = None
 
     total_pairs = args.pairs_per_gpu * world
-    solver = cb.CUDASolver(precision=args.precision, device=local, rtol=args.rtol, precond=args.precond)
+    solver = cb.CUDASolver(precision=args.precision, device=local, rtol=args.rtol, precond=args.precond,
+                           use_graph={"device": True, "chunk": "chunk", "plain": False}[args.loop])
     t_asm = time.time()
     L = src = dst = None
     if rank == 0:

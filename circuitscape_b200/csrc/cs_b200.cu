@@ -29,6 +29,8 @@ struct GraphSlot {
   cudaGraphExec_t exec = nullptr;
   int chunk = 0;
   int64_t kernels = 0, spmms = 0;   // launches inside one graph replay
+  cudaGraphExec_t loop_exec = nullptr;        // whole PCG loop as a device-side WHILE graph
+  int64_t loop_kernels = 0, loop_spmms = 0;   // launches per loop iteration
 };
 
 }  // namespace
@@ -609,7 +611,7 @@ void launch_iteration(cs_b200_handle* h) {
 template <typename T, int KT>
 int run_chunk(cs_b200_handle* h, int chunk) {
   GraphSlot& gs = h->graphs[kt_index(KT)];
-  if (h->opts.use_graph > 0 && !h->profile) {
+  if (h->opts.use_graph > 0 && !h->profile) {   // use_graph == 2: host-polled chunks
     if (!gs.exec || gs.chunk != chunk) {
       if (gs.exec) cudaGraphExecDestroy(gs.exec);
       gs.exec = nullptr;
@@ -633,6 +635,49 @@ int run_chunk(cs_b200_handle* h, int chunk) {
     for (int i = 0; i < chunk; ++i) launch_iteration<T, KT>(h);
     CK(h, cudaGetLastError());
   }
+  return CS_B200_OK;
+}
+
+// The whole PCG loop of a panel as ONE graph launch: a kernel node that evaluates the loop
+// condition, then a WHILE conditional node whose body is one captured iteration followed by
+// the condition kernel.  The device decides when to stop (cg_after_precond / k_cg_update_r
+// clear ctl->nactive; itmax bounds the loop), the host neither polls nor re-launches.
+template <typename T, int KT>
+int run_loop(cs_b200_handle* h) {
+  GraphSlot& gs = h->graphs[kt_index(KT)];
+  if (!gs.loop_exec) {
+    cudaGraph_t graph;
+    CK(h, cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle cond;
+    CK(h, cudaGraphConditionalHandleCreate(&cond, graph, 0, cudaGraphCondAssignDefault));
+    cudaGraphNode_t n_pre, n_while;
+    PanelCtl* ctl = h->d_ctl;
+    void* args[] = {&cond, &ctl};
+    cudaKernelNodeParams kp = {};
+    kp.func = (void*)k_loop_cond;
+    kp.gridDim = dim3(1);
+    kp.blockDim = dim3(1);
+    kp.kernelParams = args;
+    CK(h, cudaGraphAddKernelNode(&n_pre, graph, nullptr, 0, &kp));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = cond;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    CK(h, cudaGraphAddNode(&n_while, graph, &n_pre, 1, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    const int64_t kl = h->stats.kernel_launches, sl = h->stats.spmm_launches;
+    CK(h, cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    launch_iteration<T, KT>(h);
+    k_loop_cond<<<1, 1, 0, h->stream>>>(cond, h->d_ctl);
+    CK(h, cudaStreamEndCapture(h->stream, nullptr));
+    gs.loop_kernels = h->stats.kernel_launches - kl + 1;
+    gs.loop_spmms = h->stats.spmm_launches - sl;
+    h->stats.kernel_launches = kl;
+    h->stats.spmm_launches = sl;
+    CK(h, cudaGraphInstantiate(&gs.loop_exec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  CK(h, cudaGraphLaunch(gs.loop_exec, h->stream));
   return CS_B200_OK;
 }
 
@@ -676,10 +721,21 @@ int solve_panel(cs_b200_handle* h, double rtol, int64_t itmax) {
   }
   CK(h, cudaGetLastError());
   const int chunk = h->amg ? std::min(h->opts.check_every, 4) : h->opts.check_every;
+  const bool device_loop = h->opts.use_graph == 1 && !h->profile;
+  if (device_loop) {
+    int rc = run_loop<T, KT>(h);
+    if (rc) return rc;
+  }
   for (;;) {
     CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PanelCtl), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (h->profile) harvest_profile(h);
+    if (device_loop) {
+      GraphSlot& gs = h->graphs[kt_index(KT)];
+      h->stats.kernel_launches += 1 + gs.loop_kernels * h->h_ctl->iter;
+      h->stats.spmm_launches += gs.loop_spmms * h->h_ctl->iter;
+      break;
+    }
     if (h->h_ctl->nactive == 0) break;
     int rc = run_chunk<T, KT>(h, chunk);
     if (rc) return rc;
@@ -999,7 +1055,10 @@ void cs_b200_destroy(cs_b200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& g : h->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.loop_exec) cudaGraphExecDestroy(g.loop_exec);
+  }
   if (h->owns_matrix) { cudaFree(h->d_rowptr); cudaFree(h->d_colidx); cudaFree(h->d_vals); }
   free_win(h->A0);
   for (size_t l = 0; l < h->lv.size(); ++l) {

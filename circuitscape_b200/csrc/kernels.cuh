@@ -1200,6 +1200,13 @@ k_coarse_dense(int n, const double* __restrict__ pinv, const T* __restrict__ B, 
   X[e] = (T)((a0 + a1) + (a2 + a3));
 }
 
+// loop condition of the device-side PCG loop (CUDA-graph WHILE node): keep iterating while
+// any column of the panel is active.  Runs as the node before the loop and as the last
+// node of the loop body.
+__global__ void k_loop_cond(cudaGraphConditionalHandle handle, const PanelCtl* __restrict__ ctl) {
+  cudaGraphSetConditional(handle, (ctl->nactive > 0 && ctl->iter < ctl->itmax) ? 1u : 0u);
+}
+
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------

@@ -64,7 +64,7 @@ def factor_from_device(n, nnz, rowptr, colidx, vals, solver, log_transform=False
     opts.precond = _lib.PRECOND_AMG if solver.precond == "amg" else _lib.PRECOND_JACOBI
     opts.panel_width = solver.panel_width
     opts.check_every = solver.check_every
-    opts.use_graph = 1 if solver.use_graph else -1
+    opts.use_graph = 2 if solver.use_graph == "chunk" else (1 if solver.use_graph else -1)
     opts.log_transform = 1 if log_transform else 0
     opts.window = {"auto": 0, "on": 1, "off": -1}[solver.window]
     opts.mixed = 0 if solver.mixed else -1

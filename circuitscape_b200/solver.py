@@ -38,7 +38,7 @@ class CUDASolver:
     precond: str = "amg"             # "amg" (smoothed aggregation V-cycle) | "jacobi"
     panel_width: int = 8
     check_every: int = 16
-    use_graph: bool = True
+    use_graph: object = True      # True: device-side WHILE-graph loop; "chunk": host-polled graph chunks; False: plain launches
     window: str = "auto"             # TMA-staged windowed SpMM: auto | on | off
     f32_compute: bool = False        # precision = single: keep fp32 ON THE DEVICE too (see B200Factor)
     mixed: bool = True               # fp64 + AMG: fp32 V-cycle inside fp64 CG
@@ -89,7 +89,7 @@ class B200Factor:
         opts.precond = _lib.PRECOND_AMG if solver.precond == "amg" else _lib.PRECOND_JACOBI
         opts.panel_width = solver.panel_width
         opts.check_every = solver.check_every
-        opts.use_graph = 1 if solver.use_graph else -1
+        opts.use_graph = 2 if solver.use_graph == "chunk" else (1 if solver.use_graph else -1)
         opts.log_transform = 1 if log_transform else 0
         opts.window = {"auto": 0, "on": 1, "off": -1}[solver.window]
         opts.mixed = 0 if solver.mixed else -1

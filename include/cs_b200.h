@@ -62,7 +62,9 @@ typedef struct cs_b200_opts {
   int32_t precond;        /* cs_b200_precond                                       */
   int32_t panel_width;    /* RHS columns solved together per panel: 1,2,4,8 (def 8) */
   int32_t check_every;    /* CG iterations between host convergence polls (def 16)  */
-  int32_t use_graph;      /* capture the iteration chunk in a CUDA graph (def 1)    */
+  int32_t use_graph;      /* 0/1: whole PCG loop as a device-side WHILE graph (def);
+                             2: host-polled graph chunks of check_every iterations;
+                             -1: plain launches                                       */
   double atol;            /* absolute term of the stop test; 0 => sqrt(eps(Float64)), the
                              Krylov.jl default in force at src/core.jl:639; <0 => none */
   double resid_gate;      /* true-residual gate (def 1e-4, src/core.jl:641)         */

@@ -208,15 +208,33 @@ def test_weights_and_determinism():
     assert np.abs(outs[0][1] - outs[0][2] @ w).max() < 1e-9 * np.abs(outs[0][1]).max()
 
 
-def test_graph_and_plain_launch_agree():
+@pytest.mark.parametrize("precond", ["jacobi", "amg"])
+def test_graph_and_plain_launch_agree(precond):
+    """device-side WHILE-graph loop, host-polled graph chunks and plain launches run the
+    same iterations: identical resistances and identical per-pair iteration counts."""
     A = holey_raster(50, 50, seed=11)
     nodes = graph.focal_nodes(A.shape[0], 4, seed=2)
     src, dst = graph.all_pairs(nodes)
-    r = []
-    for ug in (True, False):
-        with cb.B200Factor(A, cb.CUDASolver(use_graph=ug)) as f:
-            r.append(f.solve_pairs(src, dst)["R"])
-    assert np.array_equal(r[0], r[1])
+    r, it = [], []
+    for ug in (True, "chunk", False):
+        with cb.B200Factor(A, cb.CUDASolver(use_graph=ug, precond=precond)) as f:
+            o = f.solve_pairs(src, dst)
+            r.append(o["R"]); it.append(o["iters"])
+            o2 = f.solve_pairs(src, dst)           # second launch of the cached graph
+            assert np.array_equal(o2["R"], o["R"])
+    assert np.array_equal(r[0], r[1]) and np.array_equal(r[0], r[2])
+    assert np.array_equal(it[0], it[1]) and np.array_equal(it[0], it[2])
+
+
+def test_device_loop_stops_at_itmax():
+    """the WHILE graph is bounded by itmax; with too few iterations the true-residual gate
+    raises the reference's error (core.jl:640-641)."""
+    A = holey_raster(60, 60, seed=12)
+    nodes = graph.focal_nodes(A.shape[0], 2, seed=2)
+    src, dst = graph.all_pairs(nodes)
+    with cb.B200Factor(A, cb.CUDASolver(precond="jacobi", itmax=3)) as f:
+        with pytest.raises(cb.B200Error):
+            f.solve_pairs(src, dst)
 
 
 def test_solve_rhs_spd_and_residual_gate():
