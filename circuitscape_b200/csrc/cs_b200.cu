@@ -94,6 +94,13 @@ struct cs_b200_handle {
   size_t flush_elems = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  // solve_rhs host<->device pipeline: panel i+1 uploads and panel i-1 downloads on two copy
+  // streams while panel i solves (column-major staging buffers, double-buffered; lazy)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  void* io_in[2] = {nullptr, nullptr};
+  void* io_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int num_sms = 148;
   int grid_spmm = 148, grid_ew = 148;
   cs_b200_opts opts{};
@@ -843,32 +850,64 @@ int pairs_panel(cs_b200_handle* h, int64_t c0, const int64_t* src, const int64_t
   return CS_B200_OK;
 }
 
+int ensure_io_pipeline(cs_b200_handle* h) {
+  if (h->s_in) return CS_B200_OK;
+  CK(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  CK(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  const size_t bytes = (size_t)h->n * h->ktmax * h->esize();
+  for (int i = 0; i < 2; ++i) {
+    CK(h, cudaMalloc(&h->io_in[i], bytes));
+    CK(h, cudaMalloc(&h->io_out[i], bytes));
+    CK(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+    CK(h, cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
+    CK(h, cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming));
+    CK(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+  }
+  return CS_B200_OK;
+}
+
+// upload of panel `ip` (columns c0 .. c0+kt) into its staging slot, on the upload stream;
+// waits until the panel that used the slot two panels ago has been transposed out of it
+template <typename T>
+int rhs_upload(cs_b200_handle* h, int ip, int64_t c0, int kt, const T* rhs) {
+  const int s = ip & 1;
+  if (ip >= 2) CK(h, cudaStreamWaitEvent(h->s_in, h->ev_used[s], 0));
+  CK(h, cudaMemcpyAsync(h->io_in[s], rhs + (size_t)c0 * h->n, (size_t)h->n * kt * sizeof(T),
+                        cudaMemcpyHostToDevice, h->s_in));
+  CK(h, cudaEventRecord(h->ev_in[s], h->s_in));
+  h->stats.h2d_bytes += (double)h->n * kt * sizeof(T);
+  return CS_B200_OK;
+}
+
 template <typename T, int KT>
-int rhs_panel(cs_b200_handle* h, int64_t c0, const T* rhs, T* lhs, double rtol, int64_t itmax,
+int rhs_panel(cs_b200_handle* h, int ip, int64_t c0, T* lhs, double rtol, int64_t itmax,
               int64_t* iters, double* relres, bool* any_fail, bool* any_maxit, std::string* msg) {
   const size_t nelem = (size_t)h->n_pad * KT;
+  const int s = ip & 1;
   PanelCtl* hc = h->h_ctl;
   std::memset(hc, 0, sizeof(PanelCtl));
   for (int c = 0; c < KT; ++c) hc->src[c] = hc->dst[c] = -1;
   CK(h, cudaMemcpyAsync(h->d_ctl, hc, sizeof(PanelCtl), cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->stage, rhs + (size_t)c0 * h->n, (size_t)h->n * KT * sizeof(T),
-                        cudaMemcpyHostToDevice, h->stream));
-  h->stats.h2d_bytes += (double)h->n * KT * sizeof(T);
   CK(h, cudaMemsetAsync(h->B, 0, nelem * sizeof(T), h->stream));
   const int tg = (int)std::min<size_t>(4096, (nelem + 255) / 256);
-  k_cm_to_panel<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->stage,
+  CK(h, cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
+  k_cm_to_panel<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->io_in[s],
                                                   (T*)h->B, KT);
+  CK(h, cudaEventRecord(h->ev_used[s], h->stream));
   h->stats.kernel_launches++;
   int rc = solve_panel<T, KT>(h, rtol, itmax);
   if (rc) return rc;
   gather_panel_status(h, KT, c0, iters, relres, itmax, any_fail, any_maxit, msg);
+  if (ip >= 2) CK(h, cudaStreamWaitEvent(h->stream, h->ev_out[s], 0));   // slot's last download done
   k_panel_to_cm<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->X,
-                                                  (T*)h->stage, h->d_ctl, 0);
+                                                  (T*)h->io_out[s], h->d_ctl, 0);
   h->stats.kernel_launches++;
-  CK(h, cudaMemcpyAsync(lhs + (size_t)c0 * h->n, h->stage, (size_t)h->n * KT * sizeof(T),
-                        cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaEventRecord(h->ev_ready[s], h->stream));
+  CK(h, cudaStreamWaitEvent(h->s_out, h->ev_ready[s], 0));
+  CK(h, cudaMemcpyAsync(lhs + (size_t)c0 * h->n, h->io_out[s], (size_t)h->n * KT * sizeof(T),
+                        cudaMemcpyDeviceToHost, h->s_out));
+  CK(h, cudaEventRecord(h->ev_out[s], h->s_out));
   h->stats.d2h_bytes += (double)h->n * KT * sizeof(T);
-  CK(h, cudaStreamSynchronize(h->stream));
   return CS_B200_OK;
 }
 
@@ -906,15 +945,31 @@ int solve_rhs_t(cs_b200_handle* h, int64_t k, const T* rhs, T* lhs, double rtol,
                 int64_t* iters, double* relres) {
   bool any_fail = false, any_maxit = false;
   std::string msg;
+  int rc = ensure_io_pipeline(h);
+  if (rc) return rc;
+  // the upload stream must not overtake work of an earlier call that still reads the slots
+  CK(h, cudaEventRecord(h->ev_used[0], h->stream));
+  CK(h, cudaStreamWaitEvent(h->s_in, h->ev_used[0], 0));
   int64_t c0 = 0;
-  while (c0 < k) {
+  int ip = 0;
+  rc = rhs_upload<T>(h, 0, 0, next_kt(k, h->ktmax), rhs);
+  while (!rc && c0 < k) {
     const int kt = next_kt(k - c0, h->ktmax);
-    int rc = 0;
-    DISPATCH_KT(kt, (rc = rhs_panel<T, KT>(h, c0, rhs, lhs, rtol, itmax, iters, relres, &any_fail,
+    const int64_t c1 = c0 + kt;
+    if (c1 < k) {   // next panel's upload overlaps this panel's solve
+      rc = rhs_upload<T>(h, ip + 1, c1, next_kt(k - c1, h->ktmax), rhs);
+      if (rc) break;
+    }
+    DISPATCH_KT(kt, (rc = rhs_panel<T, KT>(h, ip, c0, lhs, rtol, itmax, iters, relres, &any_fail,
                                            &any_maxit, &msg)));
-    if (rc) return rc;
-    c0 += kt;
+    c0 = c1;
+    ++ip;
   }
+  // drain both copy streams whatever happened: the caller owns rhs/lhs again on return
+  cudaStreamSynchronize(h->s_in);
+  cudaStreamSynchronize(h->s_out);
+  cudaStreamSynchronize(h->stream);
+  if (rc) return rc;
   if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
   if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
   return CS_B200_OK;
@@ -1084,6 +1139,13 @@ void cs_b200_destroy(cs_b200_handle* h) {
                   h->d_cum, h->d_max, h->d_ctl, h->d_partials, h->d_flush};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->io_in[i]); cudaFree(h->io_out[i]);
+    cudaEvent_t evs[] = {h->ev_in[i], h->ev_used[i], h->ev_ready[i], h->ev_out[i]};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+  }
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
