@@ -441,6 +441,31 @@ def advanced_kernel(prob: AdvancedProblem, flags: Flags, cfg=None) -> AdvancedOu
     return res
 
 
+def all_to_one_batched(factor, focal, rtol=None, shard=None):
+    """All-to-one on a graph WITHOUT finite grounds, batched on one factor.
+
+    Iteration c of the reference's all-to-one loop (src/raster/onetoall.jl:110-118,146-151)
+    ties focal node f_c to ground (Dirichlet, row/column deleted in `multiple_solver`,
+    src/raster/advanced.jl:286-300) and injects 1 A at every other focal node.  Current
+    conservation makes that the singular-Laplacian system  L v = e_others - (P-1) e_fc
+    followed by the shift v -= v[f_c] -- the pairwise trick of src/core.jl:224-232 with a
+    multi-source right-hand side -- so every iteration shares ONE operator and the P
+    solves go through hook #2 as columns of one n x P batch instead of P factorizations.
+    `factor` must hold the connected component's Laplacian.  Returns voltages (n, P'),
+    iterations and relative residuals; `shard=(rank, world)` keeps columns rank::world."""
+    focal = np.asarray(focal, dtype=np.int64)
+    cols = np.arange(len(focal)) if shard is None else np.arange(shard[0], len(focal), shard[1])
+    n = factor.n
+    rhs = np.zeros((n, len(cols)), dtype=factor.io_dtype, order="F")
+    for j, c in enumerate(cols):
+        rhs[focal, j] = 1.0
+        rhs[focal[c], j] = -(len(focal) - 1.0)
+    x, iters, relres = factor.solve_rhs(rhs, rtol=rtol)
+    x = np.asarray(x).reshape(n, len(cols))
+    x -= x[focal[cols], np.arange(len(cols))][None, :]
+    return x, iters, relres, cols
+
+
 # ---------------------------------------------------------------------------
 # one-to-all / all-to-one  (src/raster/onetoall.jl) -- callers of the advanced kernel
 # ---------------------------------------------------------------------------

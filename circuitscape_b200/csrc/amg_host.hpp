@@ -65,30 +65,77 @@ inline Csr transpose(const Csr& a) {
   return t;
 }
 
-// C = A * B (Gustavson, dense marker per output row; columns sorted on output)
-inline Csr spgemm(const Csr& a, const Csr& b) {
+// C = A * B (Gustavson, dense marker per output row; columns sorted on output).  Rows are
+// dealt to OpenMP threads in contiguous chunks and the per-chunk results concatenated, so
+// the result does not depend on the thread count.  `max_nnz` > 0 is a budget: once the
+// product has more entries the multiplication is abandoned and `*overflow` set (the
+// caller is only probing whether coarsening pays, see build_hierarchy).
+inline Csr spgemm(const Csr& a, const Csr& b, int64_t max_nnz = 0, bool* overflow = nullptr) {
   Csr c;
   c.nrows = a.nrows; c.ncols = b.ncols;
   c.ptr.assign(c.nrows + 1, 0);
-  std::vector<int> marker(b.ncols, -1);
-  std::vector<double> acc(b.ncols, 0.0);
-  std::vector<int> cols;
-  c.idx.reserve(a.idx.size());
-  c.val.reserve(a.idx.size());
-  for (int64_t i = 0; i < a.nrows; ++i) {
-    cols.clear();
-    for (int ja = a.ptr[i]; ja < a.ptr[i + 1]; ++ja) {
-      const int k = a.idx[ja];
-      const double av = a.val[ja];
-      for (int jb = b.ptr[k]; jb < b.ptr[k + 1]; ++jb) {
-        const int col = b.idx[jb];
-        if (marker[col] != (int)i) { marker[col] = (int)i; acc[col] = 0.0; cols.push_back(col); }
-        acc[col] += av * b.val[jb];
+  if (overflow) *overflow = false;
+  const int64_t n = a.nrows;
+  const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(256, n / 2048));
+  std::vector<std::vector<int>> cidx(nchunk);
+  std::vector<std::vector<double>> cval(nchunk);
+  int64_t total = 0;
+  bool over = false;
+#pragma omp parallel
+  {
+    std::vector<int> marker(b.ncols, -1);
+    std::vector<double> acc(b.ncols, 0.0);
+    std::vector<int> cols;
+#pragma omp for schedule(dynamic, 1)
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const int64_t r0 = n * ch / nchunk, r1 = n * (ch + 1) / nchunk;
+      std::vector<int>& oi = cidx[ch];
+      std::vector<double>& ov = cval[ch];
+      oi.reserve((size_t)(a.ptr[r1] - a.ptr[r0]));
+      ov.reserve((size_t)(a.ptr[r1] - a.ptr[r0]));
+      for (int64_t i = r0; i < r1; ++i) {
+        bool stop;
+#pragma omp atomic read
+        stop = over;
+        if (stop) break;
+        cols.clear();
+        for (int ja = a.ptr[i]; ja < a.ptr[i + 1]; ++ja) {
+          const int k = a.idx[ja];
+          const double av = a.val[ja];
+          for (int jb = b.ptr[k]; jb < b.ptr[k + 1]; ++jb) {
+            const int col = b.idx[jb];
+            if (marker[col] != (int)i) { marker[col] = (int)i; acc[col] = 0.0; cols.push_back(col); }
+            acc[col] += av * b.val[jb];
+          }
+        }
+        std::sort(cols.begin(), cols.end());
+        for (int col : cols) { oi.push_back(col); ov.push_back(acc[col]); }
+        c.ptr[i + 1] = (int)cols.size();
+        if (max_nnz > 0) {
+          int64_t t;
+#pragma omp atomic capture
+          { total += (int64_t)cols.size(); t = total; }
+          if (t > max_nnz) {
+#pragma omp atomic write
+            over = true;
+          }
+        }
       }
     }
-    std::sort(cols.begin(), cols.end());
-    for (int col : cols) { c.idx.push_back(col); c.val.push_back(acc[col]); }
-    c.ptr[i + 1] = (int)c.idx.size();
+  }
+  if (over) {
+    if (overflow) *overflow = true;
+    c.ptr.assign(c.nrows + 1, 0);
+    return c;
+  }
+  for (int64_t i = 0; i < n; ++i) c.ptr[i + 1] += c.ptr[i];
+  c.idx.resize((size_t)c.ptr[n]);
+  c.val.resize((size_t)c.ptr[n]);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int64_t r0 = n * ch / nchunk;
+    std::copy(cidx[ch].begin(), cidx[ch].end(), c.idx.begin() + c.ptr[r0]);
+    std::copy(cval[ch].begin(), cval[ch].end(), c.val.begin() + c.ptr[r0]);
   }
   return c;
 }
@@ -269,14 +316,17 @@ inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 2
       if (!placed) { P.idx.push_back(mine); P.val.push_back(tv); }
       P.ptr[i + 1] = (int)P.idx.size();
     }
-    Csr R = transpose(P);
-    Csr AP = spgemm(lv.A, P);
-    Csr Ac = spgemm(R, AP);
     // expander-like graphs (power-law networks) densify under smoothed aggregation: a coarse
     // operator with more entries than the one it came from buys nothing on a bandwidth-bound
     // machine -- stop here (the cycle ends at this level; with no level at all the solver is
-    // plain Jacobi-PCG)
-    if (Ac.nnz() > lv.A.nnz()) break;
+    // plain Jacobi-PCG, which such graphs like: 27 iterations on a 2e5-node BA graph).  The
+    // products carry an nnz budget so that finding this out costs O(nnz), not a dense fill.
+    bool over = false;
+    Csr AP = spgemm(lv.A, P, 4 * lv.A.nnz(), &over);
+    if (over) break;
+    Csr R = transpose(P);
+    Csr Ac = spgemm(R, AP, lv.A.nnz(), &over);
+    if (over || Ac.nnz() > lv.A.nnz()) break;
     lv.P = std::move(P);
     lv.R = std::move(R);
     h.levels.emplace_back();

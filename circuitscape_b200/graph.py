@@ -177,6 +177,35 @@ def stencil_laplacian_from_conductance(g, four_neighbors=False, avg_res=False, d
     return L
 
 
+def power_law_laplacian(n, m=5, seed=11, dtype=np.float64):
+    """Synthetic network-mode graph of SURVEY.md §8d / BASELINE config C5: preferential
+    attachment (Barabasi-Albert style, m edges per new node, grown in batches that sample
+    the degree-proportional endpoint list as of the batch start), conductances U[0.1, 1].
+    Returns the CSR Laplacian of the (connected) graph.  The reference would get the same
+    matrix from a 3-column network file through `laplacian!` (src/core.jl:608-624)."""
+    rng = np.random.default_rng(seed)
+    m0 = m + 1
+    src = [np.repeat(np.arange(1, m0), np.arange(1, m0))]
+    dst = [np.concatenate([np.arange(i) for i in range(1, m0)])]
+    ends = np.concatenate([src[0], dst[0]])
+    v0 = m0
+    while v0 < n:
+        nb = int(min(n - v0, max(1, v0 // 16)))
+        v = np.repeat(np.arange(v0, v0 + nb), m)
+        t = ends[rng.integers(0, len(ends), size=nb * m)]
+        key = np.unique(v.astype(np.int64) * n + t)          # drop repeated targets of a node
+        v, t = key // n, key % n
+        src.append(v); dst.append(t)
+        ends = np.concatenate([ends, v, t])
+        v0 += nb
+    s_, d_ = np.concatenate(src), np.concatenate(dst)
+    w = rng.uniform(0.1, 1.0, len(s_))
+    A = sp.coo_matrix((np.r_[w, w], (np.r_[s_, d_], np.r_[d_, s_])), shape=(n, n)).tocsr()
+    L = (sp.diags(np.asarray(A.sum(axis=1)).ravel()) - A).tocsr().astype(dtype)
+    L.sort_indices()
+    return L
+
+
 def focal_nodes(n, count, seed=7):
     """`count` distinct node ids (0-based) -- rng(7) as in SURVEY.md §8d."""
     rng = np.random.default_rng(seed)

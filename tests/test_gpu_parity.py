@@ -281,6 +281,26 @@ def test_solve_rhs_pipeline_many_panels():
     assert np.abs(Lr @ X - B).max() / np.abs(B).max() < 1e-4
 
 
+@pytest.mark.parametrize("precond", ["jacobi", "amg"])
+def test_network_all_to_one_batched(precond):
+    """config C5 in small: power-law graph (hub rows -> direct-gather blocks), every
+    all-to-one iteration as a column of one batch; voltages equal the grounded direct solve."""
+    import scipy.sparse.linalg as spla
+    from circuitscape_b200 import core
+    n = 4000
+    L = graph.power_law_laplacian(n, m=5, seed=11)
+    focal = graph.focal_nodes(n, 11, seed=7)
+    with cb.B200Factor(L, cb.CUDASolver(precond=precond, rtol=1e-10)) as f:
+        V, it, rr, cols = core.all_to_one_batched(f, focal)
+    assert rr.max() < 1e-6 and it.max() < 200
+    for c, g in enumerate(focal):
+        keep = np.setdiff1d(np.arange(n), [g])
+        b = np.zeros(n); b[focal] = 1.0
+        v = np.zeros(n)
+        v[keep] = spla.splu(L[keep][:, keep].tocsc()).solve(b[keep])
+        assert np.abs(V[:, c] - v).max() < 1e-6 * np.abs(v).max()
+
+
 def test_bad_pairs_rejected():
     A = holey_raster(10, 10, seed=1)
     with cb.B200Factor(A, cb.CUDASolver()) as f:

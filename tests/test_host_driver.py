@@ -65,3 +65,51 @@ def test_solver_selection():
     assert cb.get_solver({"solver": "b200", "precision": "single"}).dtype == np.float32
     with pytest.raises(ValueError):
         cb.get_solver({"solver": "cholmod"})
+
+
+# ---------------------------------------------------------------------------
+# network-mode synthetic graph (config C5) and the batched all-to-one identity
+# ---------------------------------------------------------------------------
+def test_power_law_laplacian_shape():
+    import scipy.sparse as sp
+    from circuitscape_b200 import graph
+    L = graph.power_law_laplacian(20000, m=5, seed=11)
+    assert L.shape == (20000, 20000)
+    assert abs(L - L.T).max() == 0
+    assert np.abs(np.asarray(L.sum(axis=1))).max() < 1e-9
+    deg = np.diff(L.indptr) - 1
+    assert deg.min() >= 1 and deg.max() > 30 * deg.mean()          # hubs
+    assert len(graph.connected_components(L)) == 1
+    off = L - sp.diags(L.diagonal())
+    assert off.data.max() < 0 and -off.data.min() <= 1.0 and -off.data.max() >= 0.1
+
+
+class _PinvFactor:
+    """singular-Laplacian solve by dense pseudo-inverse (what CG returns up to a constant)"""
+
+    def __init__(self, L):
+        self.n = L.shape[0]
+        self.io_dtype = np.float64
+        self.P = np.linalg.pinv(L.toarray())
+
+    def solve_rhs(self, rhs, rtol=None):
+        k = rhs.shape[1]
+        return self.P @ rhs + 3.25, np.zeros(k, dtype=np.int64), np.zeros(k)
+
+
+def test_all_to_one_batched_equals_grounded_solves():
+    """one singular operator + shift == deleting the ground's row/column per iteration
+    (src/raster/advanced.jl:286-300 with the sources of src/raster/onetoall.jl:110-118)"""
+    from circuitscape_b200 import graph, core
+    L = graph.power_law_laplacian(400, m=3, seed=5)
+    focal = graph.focal_nodes(400, 6, seed=2)
+    V, it, rr, cols = core.all_to_one_batched(_PinvFactor(L), focal)
+    assert V.shape == (400, 6) and list(cols) == list(range(6))
+    for c, f in enumerate(focal):
+        keep = np.setdiff1d(np.arange(400), [f])
+        b = np.zeros(400); b[focal] = 1.0
+        v = np.zeros(400)
+        v[keep] = np.linalg.solve(L[keep][:, keep].toarray(), b[keep])
+        assert np.abs(V[:, c] - v).max() < 1e-9 * np.abs(v).max()
+    V2, _, _, cols2 = core.all_to_one_batched(_PinvFactor(L), focal, shard=(1, 4))
+    assert list(cols2) == [1, 5] and np.allclose(V2, V[:, [1, 5]])
