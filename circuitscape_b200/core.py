@@ -441,7 +441,7 @@ def advanced_kernel(prob: AdvancedProblem, flags: Flags, cfg=None) -> AdvancedOu
     return res
 
 
-def all_to_one_batched(factor, focal, rtol=None, shard=None):
+def all_to_one_batched(factor, focal, rtol=None, shard=None, device_resident=False, accumulate=False):
     """All-to-one on a graph WITHOUT finite grounds, batched on one factor.
 
     Iteration c of the reference's all-to-one loop (src/raster/onetoall.jl:110-118,146-151)
@@ -450,12 +450,26 @@ def all_to_one_batched(factor, focal, rtol=None, shard=None):
     conservation makes that the singular-Laplacian system  L v = e_others - (P-1) e_fc
     followed by the shift v -= v[f_c] -- the pairwise trick of src/core.jl:224-232 with a
     multi-source right-hand side -- so every iteration shares ONE operator and the P
-    solves go through hook #2 as columns of one n x P batch instead of P factorizations.
-    `factor` must hold the connected component's Laplacian.  Returns voltages (n, P'),
-    iterations and relative residuals; `shard=(rank, world)` keeps columns rank::world."""
+    solves are columns of one batch instead of P factorizations.  `factor` must hold the
+    connected component's Laplacian; `shard=(rank, world)` keeps columns rank::world.
+
+    device_resident=False: through hook #2 (`solve_linear_system`, n x k host batch);
+        returns (voltages (n, P'), iters, relres, cols).
+    device_resident=True: through cs_b200_solve_sources -- right-hand sides are scattered
+        on the device, only the voltages at the focal nodes come back, node currents are
+        accumulated into the handle's cumulative / max vectors when `accumulate`;
+        returns (focal voltages (P', P), iters, relres, cols)."""
     focal = np.asarray(focal, dtype=np.int64)
     cols = np.arange(len(focal)) if shard is None else np.arange(shard[0], len(focal), shard[1])
     n = factor.n
+    if device_resident:
+        columns = []
+        for c in cols:
+            v = np.ones(len(focal))
+            v[c] = -(len(focal) - 1.0)
+            columns.append((focal, v))
+        o = factor.solve_sources(columns, focal[cols], probe=focal, accumulate=accumulate, rtol=rtol)
+        return o["probe_volt"], o["iters"], o["relres"], cols
     rhs = np.zeros((n, len(cols)), dtype=factor.io_dtype, order="F")
     for j, c in enumerate(cols):
         rhs[focal, j] = 1.0

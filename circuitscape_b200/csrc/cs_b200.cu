@@ -96,6 +96,14 @@ struct cs_b200_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // solve_rhs host<->device pipeline: panel i+1 uploads and panel i-1 downloads on two copy
   // streams while panel i solves (column-major staging buffers, double-buffered; lazy)
+  // cs_b200_solve_sources scratch (grown on demand)
+  long long* d_sp_rows = nullptr;
+  double* d_sp_vals = nullptr;
+  int* d_sp_ptr = nullptr;
+  size_t sp_cap = 0;
+  long long* d_probe = nullptr;
+  void* d_probe_out = nullptr;
+  size_t probe_cap = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   void* io_in[2] = {nullptr, nullptr};
   void* io_out[2] = {nullptr, nullptr};
@@ -850,6 +858,96 @@ int pairs_panel(cs_b200_handle* h, int64_t c0, const int64_t* src, const int64_t
   return CS_B200_OK;
 }
 
+// panel of cs_b200_solve_sources: like pairs_panel, with the right-hand sides scattered from
+// the caller's sparse columns and the shifted voltages of the probe rows as the small result
+template <typename T, int KT>
+int sources_panel(cs_b200_handle* h, int64_t c0, const int64_t* colptr, const int64_t* rows,
+                  const double* vals, const int64_t* ref, const double* weight, double rtol,
+                  int64_t itmax, int64_t nprobe, T* probe_volt, T* volt, T* curr, int accumulate,
+                  int64_t* iters, double* relres, bool* any_fail, bool* any_maxit, std::string* msg) {
+  const size_t nelem = (size_t)h->n_pad * KT;
+  PanelCtl* hc = h->h_ctl;
+  std::memset(hc, 0, sizeof(PanelCtl));
+  int ent_ptr[MAXKT + 1];
+  const int64_t e0 = colptr[c0];
+  for (int c = 0; c < KT; ++c) {
+    hc->src[c] = ref[c0 + c];
+    hc->dst[c] = -1;
+    hc->weight[c] = weight ? weight[c0 + c] : 1.0;
+    ent_ptr[c] = (int)(colptr[c0 + c] - e0);
+  }
+  ent_ptr[KT] = (int)(colptr[c0 + KT] - e0);
+  const size_t nent = (size_t)ent_ptr[KT];
+  if (nent > h->sp_cap) {
+    cudaFree(h->d_sp_rows); cudaFree(h->d_sp_vals);
+    h->d_sp_rows = nullptr; h->d_sp_vals = nullptr;
+    h->sp_cap = std::max<size_t>(nent, 1024);
+    CK(h, cudaMalloc(&h->d_sp_rows, h->sp_cap * sizeof(long long)));
+    CK(h, cudaMalloc(&h->d_sp_vals, h->sp_cap * sizeof(double)));
+  }
+  if (!h->d_sp_ptr) CK(h, cudaMalloc(&h->d_sp_ptr, (MAXKT + 1) * sizeof(int)));
+  CK(h, cudaMemcpyAsync(h->d_ctl, hc, sizeof(PanelCtl), cudaMemcpyHostToDevice, h->stream));
+  CK(h, h2d(h, h->d_sp_ptr, ent_ptr, (KT + 1) * sizeof(int)));
+  if (nent) {
+    CK(h, h2d(h, h->d_sp_rows, rows + e0, nent * sizeof(long long)));
+    CK(h, h2d(h, h->d_sp_vals, vals + e0, nent * sizeof(double)));
+  }
+  h->stats.h2d_bytes += sizeof(PanelCtl) + nent * 16.0;
+  CK(h, cudaMemsetAsync(h->B, 0, nelem * sizeof(T), h->stream));
+  k_sparse_rhs<T, KT><<<1, 32, 0, h->stream>>>((T*)h->B, h->d_sp_ptr, h->d_sp_rows, h->d_sp_vals);
+  h->stats.kernel_launches++;
+  int rc = solve_panel<T, KT>(h, rtol, itmax);
+  if (rc) return rc;
+  gather_panel_status(h, KT, c0, iters, relres, itmax, any_fail, any_maxit, msg);
+  k_pair_extract<T, KT><<<1, 32, 0, h->stream>>>((const T*)h->X, h->d_ctl);
+  h->stats.kernel_launches++;
+  if (nprobe > 0 && probe_volt) {
+    k_probe<T, KT><<<(int)std::min<int64_t>(64, (nprobe * KT + 255) / 256), 256, 0, h->stream>>>(
+        (const T*)h->X, h->d_ctl, h->d_probe, (int)nprobe, (T*)h->d_probe_out);
+    h->stats.kernel_launches++;
+    CK(h, cudaMemcpyAsync(probe_volt + (size_t)c0 * nprobe, h->d_probe_out, (size_t)nprobe * KT * sizeof(T),
+                          cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (double)nprobe * KT * sizeof(T);
+  }
+  if (accumulate || curr) {
+    const int grid = (int)std::min<int64_t>(h->grid_spmm, (h->n + (NT / KT) - 1) / (NT / KT));
+    k_cur_max<T, KT><<<grid, NT, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx,
+                                                 (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
+                                                 h->d_partials);
+    k_cur_acc<T, KT><<<grid, NT, 0, h->stream>>>(
+        (int)h->n, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
+        curr ? (T*)h->AP : nullptr, (T*)h->d_cum, (T*)h->d_max, accumulate,
+        h->opts.log_transform, KT);
+    h->stats.kernel_launches += 2;
+  }
+  CK(h, cudaGetLastError());
+  const int tg = (int)std::min<size_t>(4096, (nelem + 255) / 256);
+  if (curr) {
+    k_panel_to_cm<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->AP,
+                                                    (T*)h->stage, h->d_ctl, 0);
+    h->stats.kernel_launches++;
+    CK(h, cudaMemcpyAsync(curr + (size_t)c0 * h->n, h->stage, (size_t)h->n * KT * sizeof(T),
+                          cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (double)h->n * KT * sizeof(T);
+  }
+  if (volt) {
+    k_panel_to_cm<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->X,
+                                                    (T*)h->stage, h->d_ctl, 1);
+    h->stats.kernel_launches++;
+    CK(h, cudaMemcpyAsync(volt + (size_t)c0 * h->n, h->stage, (size_t)h->n * KT * sizeof(T),
+                          cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (double)h->n * KT * sizeof(T);
+  }
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CS_B200_OK;
+}
+
+template <typename T>
+int solve_sources_t(cs_b200_handle* h, int64_t k, const int64_t* colptr, const int64_t* rows,
+                    const double* vals, const int64_t* ref, const double* weight, double rtol,
+                    int64_t itmax, int64_t nprobe, const int64_t* probe, T* probe_volt, T* volt,
+                    T* curr, int accumulate, int64_t* iters, double* relres);
+
 int ensure_io_pipeline(cs_b200_handle* h) {
   if (h->s_in) return CS_B200_OK;
   CK(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
@@ -932,6 +1030,39 @@ int solve_pairs_t(cs_b200_handle* h, int64_t k, const int64_t* src, const int64_
     DISPATCH_KT(kt, (rc = pairs_panel<T, KT>(h, c0, src, dst, weight, rtol, itmax, R, volt, curr,
                                              accumulate, iters, relres, &any_fail, &any_maxit,
                                              &msg)));
+    if (rc) return rc;
+    c0 += kt;
+  }
+  if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
+  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
+  return CS_B200_OK;
+}
+
+template <typename T>
+int solve_sources_t(cs_b200_handle* h, int64_t k, const int64_t* colptr, const int64_t* rows,
+                    const double* vals, const int64_t* ref, const double* weight, double rtol,
+                    int64_t itmax, int64_t nprobe, const int64_t* probe, T* probe_volt, T* volt,
+                    T* curr, int accumulate, int64_t* iters, double* relres) {
+  bool any_fail = false, any_maxit = false;
+  std::string msg;
+  if (nprobe > 0 && probe_volt) {
+    const size_t need = (size_t)nprobe;
+    if (need > h->probe_cap) {
+      cudaFree(h->d_probe); cudaFree(h->d_probe_out);
+      h->d_probe = nullptr; h->d_probe_out = nullptr;
+      h->probe_cap = need;
+      CK(h, cudaMalloc(&h->d_probe, need * sizeof(long long)));
+      CK(h, cudaMalloc(&h->d_probe_out, need * MAXKT * sizeof(double)));
+    }
+    CK(h, h2d(h, h->d_probe, probe, need * sizeof(long long)));
+  }
+  int64_t c0 = 0;
+  while (c0 < k) {
+    const int kt = next_kt(k - c0, h->ktmax);
+    int rc = 0;
+    DISPATCH_KT(kt, (rc = sources_panel<T, KT>(h, c0, colptr, rows, vals, ref, weight, rtol, itmax,
+                                               nprobe, probe_volt, volt, curr, accumulate, iters,
+                                               relres, &any_fail, &any_maxit, &msg)));
     if (rc) return rc;
     c0 += kt;
   }
@@ -1139,6 +1270,8 @@ void cs_b200_destroy(cs_b200_handle* h) {
                   h->d_cum, h->d_max, h->d_ctl, h->d_partials, h->d_flush};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  cudaFree(h->d_sp_rows); cudaFree(h->d_sp_vals); cudaFree(h->d_sp_ptr);
+  cudaFree(h->d_probe); cudaFree(h->d_probe_out);
   for (int i = 0; i < 2; ++i) {
     cudaFree(h->io_in[i]); cudaFree(h->io_out[i]);
     cudaEvent_t evs[] = {h->ev_in[i], h->ev_used[i], h->ev_ready[i], h->ev_out[i]};
@@ -1369,6 +1502,36 @@ int cs_b200_solve_pairs(cs_b200_handle* h, int64_t k, const int64_t* src, const 
                                        (double*)volt, (double*)curr, accumulate, iters, relres)
                : solve_pairs_t<float>(h, k, src, dst, weight, rtol, itmax, (float*)R, (float*)volt,
                                       (float*)curr, accumulate, iters, relres);
+  end_call(h);
+  return rc;
+}
+
+int cs_b200_solve_sources(cs_b200_handle* h, int64_t k, const int64_t* colptr, const int64_t* rows,
+                          const double* vals, const int64_t* ref, const double* weight,
+                          double rtol, int64_t itmax, int64_t nprobe, const int64_t* probe,
+                          void* probe_volt, void* volt, void* curr, int accumulate,
+                          int64_t* iters, double* relres) {
+  if (!h || k < 1 || !colptr || !ref || !(rtol >= 0) || itmax < 0 || nprobe < 0 ||
+      (nprobe > 0 && !probe) || colptr[0] != 0)
+    return set_err(h, CS_B200_ERR_ARG, "bad solve_sources arguments");
+  for (int64_t c = 0; c < k; ++c) {
+    if (colptr[c + 1] < colptr[c] || ref[c] < 0 || ref[c] >= h->n)
+      return set_err(h, CS_B200_ERR_ARG, "column %lld: bad colptr or reference row", (long long)c);
+  }
+  if (colptr[k] > 0 && (!rows || !vals)) return set_err(h, CS_B200_ERR_ARG, "rows/vals missing");
+  for (int64_t e = 0; e < colptr[k]; ++e)
+    if (rows[e] < 0 || rows[e] >= h->n)
+      return set_err(h, CS_B200_ERR_ARG, "entry %lld: row %lld out of range", (long long)e, (long long)rows[e]);
+  for (int64_t i = 0; i < nprobe; ++i)
+    if (probe[i] < 0 || probe[i] >= h->n) return set_err(h, CS_B200_ERR_ARG, "probe row out of range");
+  begin_call(h);
+  int rc = h->dtype == CS_B200_F64
+               ? solve_sources_t<double>(h, k, colptr, rows, vals, ref, weight, rtol, itmax, nprobe, probe,
+                                         (double*)probe_volt, (double*)volt, (double*)curr, accumulate,
+                                         iters, relres)
+               : solve_sources_t<float>(h, k, colptr, rows, vals, ref, weight, rtol, itmax, nprobe, probe,
+                                        (float*)probe_volt, (float*)volt, (float*)curr, accumulate, iters,
+                                        relres);
   end_call(h);
   return rc;
 }

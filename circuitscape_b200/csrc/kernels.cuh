@@ -1246,6 +1246,26 @@ __global__ void k_pair_extract(const T* X, PanelCtl* ctl) {
   }
 }
 
+// sparse right-hand sides of a panel: column c owns entries ent_ptr[c] .. ent_ptr[c+1]-1;
+// one thread per column adds its entries in order (deterministic, duplicates add)
+template <typename T, int KT>
+__global__ void k_sparse_rhs(T* B, const int* __restrict__ ent_ptr, const long long* __restrict__ rows,
+                             const double* __restrict__ vals) {
+  const int c = threadIdx.x;
+  if (c < KT)
+    for (int e = ent_ptr[c]; e < ent_ptr[c + 1]; ++e) B[(size_t)rows[e] * KT + c] += (T)vals[e];
+}
+
+// out[c][i] = X[probe[i]][c] - xsrc[c]   (voltages at the probe rows after the shift)
+template <typename T, int KT>
+__global__ void k_probe(const T* __restrict__ X, const PanelCtl* __restrict__ ctl,
+                        const long long* __restrict__ probe, int nprobe, T* __restrict__ out) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nprobe * KT; e += gridDim.x * blockDim.x) {
+    const int c = e / nprobe, i = e % nprobe;
+    out[e] = (T)((double)X[(size_t)probe[i] * KT + c] - ctl->xsrc[c]);
+  }
+}
+
 // staging (column-major n x KT, leading dimension ld) <-> panel (row-major n_pad x KT)
 template <typename T, int KT>
 __global__ void k_cm_to_panel(int n, size_t ld, const T* __restrict__ cm, T* __restrict__ panel,

@@ -205,6 +205,44 @@ class B200Factor:
             curr = None if curr is None else curr.astype(self.io_dtype)
         return dict(R=R, volt=volt, curr=curr, iters=iters, relres=relres)
 
+    def solve_sources(self, columns, ref, probe=None, weight=None, want_volt=False, want_curr=False,
+                      accumulate=False, rtol=None, itmax=None, raise_on_residual=True):
+        """Batched solve with sparse right-hand sides, device-resident
+        (cs_b200_solve_sources).  columns: list of (rows, values) per right-hand side
+        (0-based rows); ref[c]: row whose voltage is subtracted (the ground).  Returns dict
+        with probe_volt (k, len(probe))|None, volt, curr, iters, relres."""
+        k = len(columns)
+        colptr = np.zeros(k + 1, dtype=np.int64)
+        for c, (r, _) in enumerate(columns):
+            colptr[c + 1] = colptr[c] + len(r)
+        rows = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int64) for r, _ in columns])
+                                    if k else np.zeros(0), dtype=np.int64)
+        vals = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for _, v in columns])
+                                    if k else np.zeros(0), dtype=np.float64)
+        ref = np.ascontiguousarray(ref, dtype=np.int64)
+        assert len(ref) == k and len(rows) == len(vals) == colptr[-1]
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        pr = None if probe is None else np.ascontiguousarray(probe, dtype=np.int64)
+        npr = 0 if pr is None else len(pr)
+        pv = np.zeros((k, npr), dtype=self.dtype) if npr else None
+        volt = np.empty((self.n, k), dtype=self.dtype, order="F") if want_volt else None
+        curr = np.empty((self.n, k), dtype=self.dtype, order="F") if want_curr else None
+        iters = np.zeros(k, dtype=np.int64)
+        relres = np.zeros(k, dtype=np.float64)
+        rc = self._lib.cs_b200_solve_sources(self._h, k, _lib._ptr(colptr), _lib._ptr(rows), _lib._ptr(vals),
+                                             _lib._ptr(ref), _lib._ptr(w),
+                                             self.solver.rtol if rtol is None else rtol,
+                                             self.solver.itmax if itmax is None else itmax,
+                                             npr, _lib._ptr(pr), _lib._ptr(pv), _lib._ptr(volt),
+                                             _lib._ptr(curr), 1 if accumulate else 0, _lib._ptr(iters),
+                                             _lib._ptr(relres))
+        self._raise(rc, raise_on_residual)
+        if self.io_dtype != self.dtype:
+            pv = None if pv is None else pv.astype(self.io_dtype)
+            volt = None if volt is None else volt.astype(self.io_dtype)
+            curr = None if curr is None else curr.astype(self.io_dtype)
+        return dict(probe_volt=pv, volt=volt, curr=curr, iters=iters, relres=relres)
+
     def read_currents(self, want_max=True):
         cum = np.empty(self.n, dtype=self.dtype)
         mx = np.empty(self.n, dtype=self.dtype) if want_max else None

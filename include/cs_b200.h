@@ -19,7 +19,7 @@
  * src/out.jl:178-290 accumulated into cumulative / max maps src/out.jl:100-107)
  * is offered as ONE device-resident call so n x k voltages never cross PCIe:
  *
- *        -> cs_b200_solve_pairs  + cs_b200_read_currents
+ *        -> cs_b200_solve_pairs / cs_b200_solve_sources  + cs_b200_read_currents
  *
  * All entry points use plain pointers and sizes; every function returns 0 on
  * success or a negative cs_b200_status; cs_b200_last_error() gives the text.
@@ -145,6 +145,23 @@ int cs_b200_solve_pairs(cs_b200_handle* h, int64_t k, const int64_t* src, const 
                         const double* weight, double rtol, int64_t itmax, void* R,
                         void* volt, void* curr, int accumulate, int64_t* iters,
                         double* relres);
+
+/* Batched solve with SPARSE right-hand sides, device-resident -- the advanced-mode kernel
+ * (src/raster/advanced.jl:274-305) for source/ground sets without finite grounds, and
+ * the all-to-one loop built on it (src/raster/onetoall.jl:110-118,146-151):
+ *   column c:  b = sum_e vals[e] * e_rows[e]   for e in colptr[c] .. colptr[c+1]-1
+ *              A v = b ;  v -= v[ref[c]]
+ * A Dirichlet ground at ref[c] with the other entries as current sources is expressed on
+ * the singular Laplacian by giving ref[c] the entry  -(sum of the sources)  (current
+ * conservation), exactly as the pairwise driver does with  -1 / +1 ; duplicates of a row
+ * within a column add.  Nothing of size n crosses PCIe unless volt / curr are requested.
+ * probe: nprobe rows whose shifted voltages are returned in probe_volt (host, k x nprobe,
+ * row-major, dtype); may be NULL / 0.  volt, curr, accumulate, weight: as in solve_pairs.  */
+int cs_b200_solve_sources(cs_b200_handle* h, int64_t k, const int64_t* colptr, const int64_t* rows,
+                          const double* vals, const int64_t* ref, const double* weight,
+                          double rtol, int64_t itmax, int64_t nprobe, const int64_t* probe,
+                          void* probe_volt, void* volt, void* curr, int accumulate,
+                          int64_t* iters, double* relres);
 
 /* Cumulative / max node-current vectors (n values of dtype each; either may be
  * NULL).  max is initialised to -9999 like src/utils.jl:124.                        */

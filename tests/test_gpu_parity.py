@@ -284,21 +284,45 @@ def test_solve_rhs_pipeline_many_panels():
 @pytest.mark.parametrize("precond", ["jacobi", "amg"])
 def test_network_all_to_one_batched(precond):
     """config C5 in small: power-law graph (hub rows -> direct-gather blocks), every
-    all-to-one iteration as a column of one batch; voltages equal the grounded direct solve."""
+    all-to-one iteration as a column of one batch; voltages equal the grounded direct
+    solve, through hook #2 and through the device-resident sparse-RHS driver."""
     import scipy.sparse.linalg as spla
     from circuitscape_b200 import core
-    n = 4000
+    n = 1500
     L = graph.power_law_laplacian(n, m=5, seed=11)
     focal = graph.focal_nodes(n, 11, seed=7)
     with cb.B200Factor(L, cb.CUDASolver(precond=precond, rtol=1e-10)) as f:
         V, it, rr, cols = core.all_to_one_batched(f, focal)
+        FV, it2, rr2, _ = core.all_to_one_batched(f, focal, device_resident=True, accumulate=True)
+        cum, mx = f.read_currents()
+        o = f.solve_sources([(focal, np.r_[-10.0, np.ones(10)])], [focal[0]], probe=focal[:3],
+                            want_volt=True, want_curr=True)
     assert rr.max() < 1e-6 and it.max() < 200
-    for c, g in enumerate(focal):
+    assert np.array_equal(it, it2)
+    assert np.abs(FV - V[focal].T).max() < 1e-9 * np.abs(V).max()
+    assert np.abs(o["volt"][:, 0] - V[:, 0]).max() < 1e-9 * np.abs(V).max()
+    assert np.allclose(o["probe_volt"][0], V[focal[:3], 0], rtol=0, atol=1e-9 * np.abs(V).max())
+    cum_ref = np.zeros(n)
+    for c in (0, 4, 10):
+        g = focal[c]
         keep = np.setdiff1d(np.arange(n), [g])
         b = np.zeros(n); b[focal] = 1.0
         v = np.zeros(n)
         v[keep] = spla.splu(L[keep][:, keep].tocsc()).solve(b[keep])
         assert np.abs(V[:, c] - v).max() < 1e-6 * np.abs(v).max()
+    for c in range(len(focal)):
+        cum_ref += core.node_currents_host(L, V[:, c])
+    assert np.abs(cum - cum_ref).max() < 1e-8 * np.abs(cum_ref).max()
+    assert np.abs(o["curr"][:, 0] - core.node_currents_host(L, V[:, 0])).max() < 1e-8 * np.abs(cum_ref).max()
+
+
+def test_solve_sources_rejects_bad_input():
+    A = holey_raster(20, 20, seed=3)
+    with cb.B200Factor(A, cb.CUDASolver()) as f:
+        with pytest.raises(cb.B200Error):
+            f.solve_sources([([0, A.shape[0]], [1.0, -1.0])], [0])
+        with pytest.raises(cb.B200Error):
+            f.solve_sources([([0, 1], [1.0, -1.0])], [-1])
 
 
 def test_bad_pairs_rejected():
