@@ -8,7 +8,7 @@
 //   strength      every off-diagonal nonzero (symmetric strength, theta = 0)
 //   aggregation   greedy root + neighbourhood, leftovers join a neighbour
 //   tentative T   piecewise constant, columns normalised (candidate = ones)
-//   prolongator   P = (I - (4/3)/rho * D^-1 A) T,  rho ~ 1.1 lambda_max(D^-1 A) (power iteration),
+//   prolongator   P = (I - (4/3)/rho * D^-1 A) T,  rho ~ lambda_max(D^-1 A) (power iteration),
 //                 capped by ||D^-1 A||_inf
 //   coarse op     A_c = P^T A P  (Galerkin)
 //   coarsest      (<= 200 nodes) dense symmetric pseudo-inverse, cyclic Jacobi eigen-solver
@@ -20,8 +20,23 @@
 #include <cstdint>
 #include <numeric>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace csb_amg {
+
+// OpenMP team size for a loop over `work` items: serial below 2e5 (the golden-test sized
+// components would only pay fork/join latency), at most 16 threads above (setup shares the
+// host with the other ranks of a multi-GPU job)
+inline int team(int64_t work) {
+#ifdef _OPENMP
+  return work < 200000 ? 1 : std::min(16, omp_get_max_threads());
+#else
+  (void)work; return 1;
+#endif
+}
+
 
 struct Csr {
   int64_t nrows = 0, ncols = 0;
@@ -82,7 +97,7 @@ inline Csr spgemm(const Csr& a, const Csr& b, int64_t max_nnz = 0, bool* overflo
   std::vector<std::vector<double>> cval(nchunk);
   int64_t total = 0;
   bool over = false;
-#pragma omp parallel
+#pragma omp parallel num_threads(team(a.nnz()))
   {
     std::vector<int> marker(b.ncols, -1);
     std::vector<double> acc(b.ncols, 0.0);
@@ -132,7 +147,7 @@ inline Csr spgemm(const Csr& a, const Csr& b, int64_t max_nnz = 0, bool* overflo
   for (int64_t i = 0; i < n; ++i) c.ptr[i + 1] += c.ptr[i];
   c.idx.resize((size_t)c.ptr[n]);
   c.val.resize((size_t)c.ptr[n]);
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(team(a.nnz()))
   for (int ch = 0; ch < nchunk; ++ch) {
     const int64_t r0 = n * ch / nchunk;
     std::copy(cidx[ch].begin(), cidx[ch].end(), c.idx.begin() + c.ptr[r0]);
@@ -254,15 +269,15 @@ inline std::vector<double> dense_pinv(const Csr& a) {
 }
 
 // dinv = 1/diag(A);  rho = estimate of lambda_max(D^-1 A): 20 power iterations (Rayleigh
-// quotient in the D inner product, fixed start vector => deterministic) with a 10 % safety
-// margin, capped by the rigorous bound ||D^-1 A||_inf.  For raster stencils the bound is 2
+// quotient in the D inner product, fixed start vector => deterministic), kept inside
+// [0.7, 1] x the rigorous bound ||D^-1 A||_inf.  For raster stencils the bound is 2
 // while lambda_max ~ 1.6; the sharper value gives a larger Jacobi / prolongator-smoothing
 // weight (omega = (4/3)/rho) and ~12 % fewer CG iterations.
 inline void diag_and_rho(const Csr& a, std::vector<double>& dinv, double& rho) {
   const int64_t n = a.nrows;
   dinv.assign(n, 0.0);
   double rho_inf = 0.0;
-#pragma omp parallel for reduction(max : rho_inf) schedule(static)
+#pragma omp parallel for reduction(max : rho_inf) schedule(static) num_threads(team(a.nnz()))
   for (int64_t i = 0; i < n; ++i) {
     double d = 0.0, s = 0.0;
     for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j) {
@@ -282,7 +297,7 @@ inline void diag_and_rho(const Csr& a, std::vector<double>& dinv, double& rho) {
     double num = 0.0, den = 0.0;
     const int nchunk = 64;   // fixed partition => the sums do not depend on the thread count
     double pn[nchunk], pd[nchunk];
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(a.nnz()))
     for (int ch = 0; ch < nchunk; ++ch) {
       double sn = 0.0, sd = 0.0;
       for (int64_t i = n * ch / nchunk; i < n * (ch + 1) / nchunk; ++i) {
@@ -303,7 +318,10 @@ inline void diag_and_rho(const Csr& a, std::vector<double>& dinv, double& rho) {
     const double inv = 1.0 / nrm;
     for (int64_t i = 0; i < n; ++i) x[i] = y[i] * inv;
   }
-  rho = lam > 0.0 ? std::min(rho_inf, 1.1 * lam) : rho_inf;
+  // lam is a Rayleigh quotient, i.e. a LOWER bound of lambda_max <= rho_inf.  The floor
+  // 0.7 rho_inf keeps omega * lambda_max <= (4/3)/0.7 < 2 whatever the estimate did, so the
+  // Jacobi smoother stays convergent and the V-cycle positive definite.
+  rho = lam > 0.0 ? std::min(rho_inf, std::max(lam, 0.7 * rho_inf)) : rho_inf;
 }
 
 inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 200) {

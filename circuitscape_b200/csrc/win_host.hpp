@@ -97,7 +97,7 @@ inline Windowed build(const int* rowptr, const int* colidx, int64_t nrows,
   w.perm_off.assign((size_t)ent_off[nb] + 8, -1);
   w.roff.assign((size_t)roff_off[nb] + 8, 0);
   int64_t nwin = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : nwin)
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : nwin) num_threads(nb < 512 ? 1 : 16)
   for (int b = 0; b < nb; ++b) {
     BlockMeta& m = w.meta[b];
     const int r0 = bstart[b], r1 = bstart[b + 1];
