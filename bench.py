@@ -347,10 +347,9 @@ def main():
         factor.profile_spmm(True)
         factor.reset_currents()
         factor.solve_pairs(msrc, mdst, accumulate=True)     # rank-local repeat of the step's solve
+        pbytes = factor.profile_bytes()
         pms, pl = factor.profile_spmm(False)
         sv = 8 if args.precision == "double" else 4
-        kt = min(8, k)
-        # launches are a mix of panel widths (8 + 2 for 10 pairs): bytes per launch averaged
         widths = []
         rem = k
         while rem > 0:
@@ -358,23 +357,27 @@ def main():
             while w > rem:
                 w //= 2
             widths.append(w); rem -= w
-        it_per_col = out["iters"]
-        pos, bytes_total, ln = 0, 0.0, 0
-        for w in widths:
-            its = int(it_per_col[pos:pos + w].max()) + 1      # + the residual SpMM
-            chunks = -(-int(it_per_col[pos:pos + w].max()) // 16) * 16 + 1
-            bytes_total += chunks * b_spmm(n, nnz, w, sv)
-            ln += chunks
-            pos += w
-        avg_bytes = bytes_total / max(ln, 1)
-        achieved = avg_bytes / (pms / max(pl, 1) * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_spmm<f64,KT>(CG mode) over panels " + "+".join(map(str, widths)),
+        avg_bytes = pbytes / max(pl, 1)
+        achieved = pbytes / (pms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath)).get("c2_finest_level_spmm")
+            if tj:
+                traffic = tj.get("traffic_bytes_per_launch")
+        roof = {"bound": "hbm",
+                "kernel": "k_spmm_win on the finest-level operator, every epilogue of the AMG-PCG iteration "
+                          "(fp64 CG / residual gate, fp32 residual + Jacobi sweep of the V-cycle), panels "
+                          + "+".join(map(str, widths)),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "launches": int(pl),
+                "traffic": traffic, "peak_source": peak_src, "launches": int(pl),
                 "avg_launch_ms": pms / max(pl, 1), "algorithmic_bytes_per_launch": avg_bytes,
                 "spmm_share_of_step": pms / (ms / args.steps),
-                "note": "per-launch CUDA events on the solve stream in an instrumented repeat of the "
-                        "timed step; 1000^2 operands are partly L2-resident (see spmv_1e7 for HBM-bound)"}
+                "note": "per-launch CUDA events on the solve stream in an instrumented repeat of the timed "
+                        "step (plain launches, same kernels as the graph); bytes = nnz(s_v+4)+(n+1)4+panel "
+                        "passes summed per launch by the library; traffic = ncu dram bytes per launch averaged "
+                        "over the same kernels (profiles/r1_traffic.json); 1000^2 operands are partly "
+                        "L2-resident (see spmv_1e7 for the HBM-bound size)"}
         for kk in (1, 8):
             t_it = factor.bench_cg_iter(kk, reps=50)
             b_it = b_spmm(n, nnz, kk, sv) + 8 * n * kk * sv + 2 * n * sv

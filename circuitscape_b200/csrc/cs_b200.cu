@@ -120,6 +120,7 @@ struct cs_b200_handle {
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
   double prof_ms = 0.0;
+  double prof_bytes = 0.0;   // algorithmic bytes of the timed launches (DESIGN.md §4 formula)
   int64_t prof_launches = 0;
   std::string err;
   size_t esize() const { return dtype == CS_B200_F64 ? 8 : 4; }
@@ -469,6 +470,14 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
     }
     e0 = h->prof_ev[h->prof_used++];
     e1 = h->prof_ev[h->prof_used++];
+    // nnz (s_v + 4) + (n + 1) 4 + X once + Y once (+ B for the residual / sweep epilogues,
+    // + 1/diag for the sweeps)
+    double bytes = (double)m.nnz * (sizeof(T) + 4) + (double)(m.nrows + 1) * 4 +
+                   2.0 * (double)m.nrows * KT * sizeof(T);
+    if (MODE == SP_RESNORM || MODE == SP_RES || MODE == SP_JACOBI || MODE == SP_JACOBI_DOT)
+      bytes += (double)m.nrows * KT * sizeof(T);
+    if (MODE == SP_JACOBI || MODE == SP_JACOBI_DOT) bytes += (double)m.nrows * sizeof(T);
+    h->prof_bytes += bytes;
     cudaEventRecord(e0, h->stream);
   }
   const SpmmEpi<T> ep{B, dinv, (T)omega, h->d_ctl, h->d_partials};
@@ -1333,7 +1342,14 @@ int cs_b200_profile_spmm(cs_b200_handle* h, int enable, double* total_ms, int64_
     h->prof_ms = 0.0;
     h->prof_launches = 0;
     h->prof_used = 0;
+    h->prof_bytes = 0.0;
   }
+  return CS_B200_OK;
+}
+
+int cs_b200_profile_bytes(cs_b200_handle* h, double* algorithmic_bytes) {
+  if (!h || !algorithmic_bytes) return CS_B200_ERR_ARG;
+  *algorithmic_bytes = h->prof_bytes;
   return CS_B200_OK;
 }
 

@@ -132,6 +132,12 @@ class B200Factor:
                                                   C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
 
+    def profile_bytes(self):
+        """algorithmic bytes of the launches timed since profiling was enabled."""
+        b = C.c_double()
+        _lib.check(self._lib, self._h, self._lib.cs_b200_profile_bytes(self._h, C.byref(b)))
+        return b.value
+
     def spmv(self, x, reps=1):
         x = np.ascontiguousarray(x, dtype=self.dtype)
         y = np.empty_like(x)

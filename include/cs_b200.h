@@ -181,6 +181,10 @@ int cs_b200_stream(cs_b200_handle* h, void** stream);
  * totals; enable < 0 only reads.  *total_ms / *launches: totals since last enable.  */
 int cs_b200_profile_spmm(cs_b200_handle* h, int enable, double* total_ms, int64_t* launches);
 
+/* Algorithmic bytes (nnz (s_v+4) + (n+1) 4 + panel passes) summed over
+ * the launches timed since profiling was last enabled; read BEFORE disabling.          */
+int cs_b200_profile_bytes(cs_b200_handle* h, double* algorithmic_bytes);
+
 /* Library/ABI version: major*1000 + minor.                                          */
 int cs_b200_version(void);
 
