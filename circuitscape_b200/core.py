@@ -483,6 +483,28 @@ def all_to_one_batched(factor, focal, rtol=None, shard=None, device_resident=Fal
 # ---------------------------------------------------------------------------
 # one-to-all / all-to-one  (src/raster/onetoall.jl) -- callers of the advanced kernel
 # ---------------------------------------------------------------------------
+def compute_omniscape_current(conductance, source, ground, cs_cfg, solver=None):
+    """src/utils.jl:145-257 -- Omniscape's moving-window solve: one advanced-mode solve per
+    connected component of a conductance window, returning the node-current raster.
+
+    conductance / source / ground: 2-D arrays of one shape (NODATA or 0 conductance = no
+    node; ground values are conductances: the reference hard-wires grnd_file_is_res =
+    false, policy :rmvsrc and the average-conductance rule there, utils.jl:190-193);
+    cs_cfg: the INI dictionary (only `connect_four_neighbors_only` and the solver keys are
+    read).  `solver` overrides `get_solver(cs_cfg)`; tests pass a CPU double here."""
+    from . import graph
+    cellmap = np.array(conductance, dtype=np.float64)
+    cellmap[cellmap == NODATA] = 0.0
+    nodemap = graph.construct_node_map(cellmap, None)
+    four = _flag(cs_cfg, "connect_four_neighbors_only")
+    G = graph.laplacian(graph.construct_graph(cellmap, nodemap, False, four))
+    cc = graph.connected_components(G)
+    s, g, f = sources_and_grounds_from_maps(np.asarray(source, dtype=np.float64),
+                                            np.asarray(ground, dtype=np.float64), nodemap, G.shape[0], "rmvsrc")
+    prob = AdvancedProblem(G, cc, s, g, f, nodemap, None, cellmap, solver if solver is not None else get_solver(cs_cfg))
+    return advanced_kernel(prob, Flags(is_raster=True, is_advanced=True), cs_cfg).curmap
+
+
 def resolve_conflicts(sources, grounds, policy):
     """src/raster/advanced.jl:119-149 (`rmvall` only zeroes the sources -- pinned upstream by
     test/internal.jl:130-135)."""

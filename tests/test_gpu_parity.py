@@ -325,6 +325,42 @@ def test_solve_sources_rejects_bad_input():
             f.solve_sources([([0, 1], [1.0, -1.0])], [-1])
 
 
+def test_compute_omniscape_current_on_device():
+    """src/utils.jl:145-257 through hook #3 on the GPU; the reference's own example window
+    (test/internal.jl:5-43) and a 40x30 window with holes against a host direct solve."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from circuitscape_b200 import core
+    conductance = np.array([[1, 5, 1.], [2, 1, 1], [9, 1, 6]])
+    source = np.array([[1, 0, 0.], [0, 0, 0], [0, 1, 0]])
+    ground = np.array([[0, 0, 1.], [0, 0, 0], [0, 0, 0]])
+    cur = cb.compute_omniscape_current(conductance, source, ground,
+                                       {"connect_four_neighbors_only": "False", "solver": "cuda"})
+    assert abs(cur[0, 2] - 2.0) < 1e-6 and cur.min() >= 0
+    rng = np.random.default_rng(5)
+    g = rng.uniform(0.5, 2.0, (40, 30)); g[rng.random(g.shape) < 0.1] = 0.0
+    src = np.zeros_like(g); src[2, 3] = 1.0; src[30, 20] = 0.5
+    gnd = np.zeros_like(g); gnd[6, 1] = 2.0; gnd[35, 28] = 1.0
+    for k in (src, gnd):
+        k[g <= 0] = 0
+    cur = cb.compute_omniscape_current(g, src, gnd, {"connect_four_neighbors_only": "True", "solver": "cuda",
+                                                     "gpu_rtol": "1e-10"})
+    nodemap = graph.construct_node_map(g, None)
+    G = graph.laplacian(graph.construct_graph(g, nodemap, False, True))
+    s, gr, f = core.sources_and_grounds_from_maps(src, gnd, nodemap, G.shape[0], "rmvsrc")
+    ref = np.zeros_like(g)
+    for c in graph.connected_components(G):
+        rows = np.asarray(c) - 1
+        if s[rows].sum() == 0 or gr[rows].sum() == 0:
+            continue
+        A = G[rows][:, rows]
+        v = spla.splu((A + sp.diags(f[rows])).tocsc()).solve(s[rows])
+        nc = core.node_currents_host(A, v, f[rows])
+        for r_, val in zip(rows, nc):
+            ref[nodemap == r_ + 1] += val
+    assert np.abs(cur - ref).max() < 1e-7 * ref.max()
+
+
 def test_bad_pairs_rejected():
     A = holey_raster(10, 10, seed=1)
     with cb.B200Factor(A, cb.CUDASolver()) as f:

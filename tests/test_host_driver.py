@@ -3,6 +3,7 @@ a CPU test double standing in for the device factor -- runs without a GPU.  The
 same cases run through the real CUDA library in tests/test_gpu_parity.py."""
 import numpy as np
 import pytest
+import scipy.sparse as sp
 
 import circuitscape_b200 as cb
 from circuitscape_b200 import solver as S
@@ -113,3 +114,44 @@ def test_all_to_one_batched_equals_grounded_solves():
         assert np.abs(V[:, c] - v).max() < 1e-9 * np.abs(v).max()
     V2, _, _, cols2 = core.all_to_one_batched(_PinvFactor(L), focal, shard=(1, 4))
     assert list(cols2) == [1, 5] and np.allclose(V2, V[:, [1, 5]])
+
+
+# ---------------------------------------------------------------------------
+# compute_omniscape_current (src/utils.jl:145-257)
+# ---------------------------------------------------------------------------
+def test_compute_omniscape_current_reference_example():
+    """the reference's own call (test/internal.jl:5-43) plus a check against the oracle's
+    advanced-mode raster path on the same window."""
+    conductance = np.array([[1, 5, 1.], [2, 1, 1], [9, 1, 6]])
+    source = np.array([[1, 0, 0.], [0, 0, 0], [0, 1, 0]])
+    ground = np.array([[0, 0, 1.], [0, 0, 0], [0, 0, 0]])
+    cs_cfg = {"ground_file_is_resistances": "True", "use_direct_grounds": "False", "output_file": "temp",
+              "write_cum_cur_map_only": "False", "scenario": "Advanced", "suppress_messages": "True",
+              "connect_four_neighbors_only": "False", "solver": "cuda", "cholmod_batch_size": "1000",
+              "data_type": "raster"}
+    cur = cb.compute_omniscape_current(conductance, source, ground, cs_cfg)
+    assert cur.shape == (3, 3) and np.all(np.isfinite(cur)) and cur.min() >= 0
+    # 2 A injected, all of it leaves through the single ground cell (conductance 1 to earth)
+    assert abs(cur[0, 2] - 2.0) < 1e-9
+    # oracle: same graph, same sources/grounds
+    nodemap = co.construct_node_map(conductance, None)
+    G = co.laplacian(co.construct_graph(conductance, nodemap, False, False))
+    s, g, f = co._sources_grounds_raster(source, ground, nodemap, G.shape[0], "rmvsrc")
+    M = (G + sp.diags(f)).tocsc()
+    import scipy.sparse.linalg as spla
+    v = spla.splu(M).solve(s)
+    ref = np.zeros((3, 3))
+    nc = co.get_node_currents(G, v, f)
+    ref[nodemap > 0] = nc[nodemap[nodemap > 0] - 1]
+    assert np.abs(cur - ref).max() < 1e-9
+
+
+def test_compute_omniscape_current_window_with_holes():
+    rng = np.random.default_rng(5)
+    g = rng.uniform(0.5, 2.0, (12, 9)); g[rng.random(g.shape) < 0.15] = -9999.0
+    src = np.zeros_like(g); src[2, 3] = 1.0; src[9, 7] = 0.5
+    gnd = np.zeros_like(g); gnd[6, 1] = 2.0; gnd[11, 8] = 1.0
+    for k in (src, gnd):
+        k[g <= 0] = 0
+    cur = cb.compute_omniscape_current(g, src, gnd, {"connect_four_neighbors_only": "True", "solver": "cuda"})
+    assert cur.shape == g.shape and np.all(cur[g <= 0] == 0) and cur.max() > 0
