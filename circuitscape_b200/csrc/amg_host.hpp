@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <limits>
 #include <numeric>
 #include <vector>
 #ifdef _OPENMP
@@ -81,77 +82,75 @@ inline Csr transpose(const Csr& a) {
   return t;
 }
 
-// C = A * B (Gustavson, dense marker per output row; columns sorted on output).  Rows are
-// dealt to OpenMP threads in contiguous chunks and the per-chunk results concatenated, so
-// the result does not depend on the thread count.  `max_nnz` > 0 is a budget: once the
-// product has more entries the multiplication is abandoned and `*overflow` set (the
-// caller is only probing whether coarsening pays, see build_hierarchy).
+// C = A * B (Gustavson; columns sorted on output).  Two passes over contiguous row chunks
+// dealt to OpenMP threads: pass 1 counts the distinct columns of every output row, a prefix
+// sum sizes the result, pass 2 accumulates and writes straight into it (no per-thread
+// buffers to merge; the result does not depend on the thread count).  `max_nnz` > 0 is a
+// budget: if the product would have more entries the multiplication is abandoned after the
+// counting pass and `*overflow` set (the caller is only probing whether coarsening pays).
 inline Csr spgemm(const Csr& a, const Csr& b, int64_t max_nnz = 0, bool* overflow = nullptr) {
   Csr c;
   c.nrows = a.nrows; c.ncols = b.ncols;
   c.ptr.assign(c.nrows + 1, 0);
   if (overflow) *overflow = false;
   const int64_t n = a.nrows;
-  const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(256, n / 2048));
-  std::vector<std::vector<int>> cidx(nchunk);
-  std::vector<std::vector<double>> cval(nchunk);
-  int64_t total = 0;
-  bool over = false;
-#pragma omp parallel num_threads(team(a.nnz()))
+  const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(512, n / 1024));
+  const int nt = team(a.nnz());
+  std::vector<int64_t> chunk_nnz(nchunk, 0);
+#pragma omp parallel num_threads(nt)
   {
     std::vector<int> marker(b.ncols, -1);
-    std::vector<double> acc(b.ncols, 0.0);
-    std::vector<int> cols;
 #pragma omp for schedule(dynamic, 1)
     for (int ch = 0; ch < nchunk; ++ch) {
-      const int64_t r0 = n * ch / nchunk, r1 = n * (ch + 1) / nchunk;
-      std::vector<int>& oi = cidx[ch];
-      std::vector<double>& ov = cval[ch];
-      oi.reserve((size_t)(a.ptr[r1] - a.ptr[r0]));
-      ov.reserve((size_t)(a.ptr[r1] - a.ptr[r0]));
-      for (int64_t i = r0; i < r1; ++i) {
-        bool stop;
-#pragma omp atomic read
-        stop = over;
-        if (stop) break;
-        cols.clear();
+      int64_t tot = 0;
+      for (int64_t i = n * ch / nchunk; i < n * (ch + 1) / nchunk; ++i) {
+        int cnt = 0;
         for (int ja = a.ptr[i]; ja < a.ptr[i + 1]; ++ja) {
           const int k = a.idx[ja];
-          const double av = a.val[ja];
           for (int jb = b.ptr[k]; jb < b.ptr[k + 1]; ++jb) {
             const int col = b.idx[jb];
-            if (marker[col] != (int)i) { marker[col] = (int)i; acc[col] = 0.0; cols.push_back(col); }
-            acc[col] += av * b.val[jb];
+            if (marker[col] != (int)i) { marker[col] = (int)i; ++cnt; }
           }
         }
-        std::sort(cols.begin(), cols.end());
-        for (int col : cols) { oi.push_back(col); ov.push_back(acc[col]); }
-        c.ptr[i + 1] = (int)cols.size();
-        if (max_nnz > 0) {
-          int64_t t;
-#pragma omp atomic capture
-          { total += (int64_t)cols.size(); t = total; }
-          if (t > max_nnz) {
-#pragma omp atomic write
-            over = true;
-          }
-        }
+        c.ptr[i + 1] = cnt;
+        tot += cnt;
       }
+      chunk_nnz[ch] = tot;
     }
   }
-  if (over) {
+  int64_t total = 0;
+  for (int ch = 0; ch < nchunk; ++ch) total += chunk_nnz[ch];
+  if ((max_nnz > 0 && total > max_nnz) || total > (int64_t)std::numeric_limits<int>::max()) {
     if (overflow) *overflow = true;
     c.ptr.assign(c.nrows + 1, 0);
     return c;
   }
   for (int64_t i = 0; i < n; ++i) c.ptr[i + 1] += c.ptr[i];
-  c.idx.resize((size_t)c.ptr[n]);
-  c.val.resize((size_t)c.ptr[n]);
-#pragma omp parallel for schedule(dynamic, 1) num_threads(team(a.nnz()))
-  for (int ch = 0; ch < nchunk; ++ch) {
-    const int64_t r0 = n * ch / nchunk;
-    std::copy(cidx[ch].begin(), cidx[ch].end(), c.idx.begin() + c.ptr[r0]);
-    std::copy(cval[ch].begin(), cval[ch].end(), c.val.begin() + c.ptr[r0]);
+  c.idx.resize((size_t)total);
+  c.val.resize((size_t)total);
+#pragma omp parallel num_threads(nt)
+  {
+    std::vector<int> marker(b.ncols, -1);
+    std::vector<double> acc(b.ncols, 0.0);
+#pragma omp for schedule(dynamic, 1)
+    for (int ch = 0; ch < nchunk; ++ch) {
+      for (int64_t i = n * ch / nchunk; i < n * (ch + 1) / nchunk; ++i) {
+        int* oc = c.idx.data() + c.ptr[i];
+        int cnt = 0;
+        for (int ja = a.ptr[i]; ja < a.ptr[i + 1]; ++ja) {
+          const int k = a.idx[ja];
+          const double av = a.val[ja];
+          for (int jb = b.ptr[k]; jb < b.ptr[k + 1]; ++jb) {
+            const int col = b.idx[jb];
+            if (marker[col] != (int)i) { marker[col] = (int)i; acc[col] = 0.0; oc[cnt++] = col; }
+            acc[col] += av * b.val[jb];
+          }
+        }
+        std::sort(oc, oc + cnt);
+        double* ov = c.val.data() + c.ptr[i];
+        for (int q = 0; q < cnt; ++q) ov[q] = acc[oc[q]];
+      }
+    }
   }
   return c;
 }
@@ -268,7 +267,7 @@ inline std::vector<double> dense_pinv(const Csr& a) {
   return out;
 }
 
-// dinv = 1/diag(A);  rho = estimate of lambda_max(D^-1 A): 20 power iterations (Rayleigh
+// dinv = 1/diag(A);  rho = estimate of lambda_max(D^-1 A): 8 power iterations (Rayleigh
 // quotient in the D inner product, fixed start vector => deterministic), kept inside
 // [0.7, 1] x the rigorous bound ||D^-1 A||_inf.  For raster stencils the bound is 2
 // while lambda_max ~ 1.6; the sharper value gives a larger Jacobi / prolongator-smoothing
@@ -293,29 +292,30 @@ inline void diag_and_rho(const Csr& a, std::vector<double>& dinv, double& rho) {
   std::vector<double> x(n), y(n);
   for (int64_t i = 0; i < n; ++i) x[i] = dinv[i] != 0.0 ? 1.0 + (double)((i * 2654435761ULL) % 1024) / 1024.0 * ((i & 1) ? 1.0 : -1.0) : 0.0;
   double lam = 0.0;
-  for (int it = 0; it < 20; ++it) {
-    double num = 0.0, den = 0.0;
-    const int nchunk = 64;   // fixed partition => the sums do not depend on the thread count
-    double pn[nchunk], pd[nchunk];
-#pragma omp parallel for schedule(static) num_threads(team(a.nnz()))
+  const int nchunk = 64;   // fixed partition => the sums do not depend on the thread count
+  const int nt = team(a.nnz());
+  for (int it = 0; it < 8; ++it) {
+    double pn[nchunk], pd[nchunk], pm[nchunk];
+#pragma omp parallel for schedule(static) num_threads(nt)
     for (int ch = 0; ch < nchunk; ++ch) {
-      double sn = 0.0, sd = 0.0;
+      double sn = 0.0, sd = 0.0, sm = 0.0;
       for (int64_t i = n * ch / nchunk; i < n * (ch + 1) / nchunk; ++i) {
         double acc = 0.0;
         for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j) acc += a.val[j] * x[a.idx[j]];
         sn += x[i] * acc;                                   // x' A x
         sd += dinv[i] != 0.0 ? x[i] * x[i] / dinv[i] : 0.0; // x' D x
         y[i] = dinv[i] * acc;
+        sm = std::max(sm, std::fabs(y[i]));
       }
-      pn[ch] = sn; pd[ch] = sd;
+      pn[ch] = sn; pd[ch] = sd; pm[ch] = sm;
     }
-    for (int ch = 0; ch < nchunk; ++ch) { num += pn[ch]; den += pd[ch]; }
+    double num = 0.0, den = 0.0, nrm = 0.0;
+    for (int ch = 0; ch < nchunk; ++ch) { num += pn[ch]; den += pd[ch]; nrm = std::max(nrm, pm[ch]); }
     if (!(den > 0.0)) break;
     lam = num / den;
-    double nrm = 0.0;
-    for (int64_t i = 0; i < n; ++i) nrm = std::max(nrm, std::fabs(y[i]));
     if (!(nrm > 0.0)) break;
     const double inv = 1.0 / nrm;
+#pragma omp parallel for schedule(static) num_threads(nt)
     for (int64_t i = 0; i < n; ++i) x[i] = y[i] * inv;
   }
   // lam is a Rayleigh quotient, i.e. a LOWER bound of lambda_max <= rho_inf.  The floor

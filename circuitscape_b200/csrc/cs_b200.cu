@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -127,6 +128,19 @@ struct cs_b200_handle {
 };
 
 namespace {
+
+// CS_B200_VERBOSE=1: one stderr line per setup phase (host hierarchy, windows, uploads)
+struct Tick {
+  bool on = std::getenv("CS_B200_VERBOSE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void operator()(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[cs_b200 setup] %-28s %8.1f ms\n", what,
+                 std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 int set_err(cs_b200_handle* h, int code, const char* fmt, ...) {
   char buf[1024];
@@ -317,7 +331,9 @@ int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<i
   a0.ptr = rp;
   a0.idx = ci;
   a0.val.assign(vals_host, vals_host + h->nnz);
+  Tick tick;
   csb_amg::Hierarchy hier = csb_amg::build_hierarchy(std::move(a0));
+  tick("host hierarchy");
   h->amg_opc = hier.operator_complexity();
   const int nl = (int)hier.levels.size();
   // fp64 handles run the V-cycle in fp32 (opts.mixed: 0 auto = on, -1 off): the preconditioner
@@ -325,6 +341,7 @@ int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<i
   h->mixed = nl > 1 && sizeof(T) == 8 && h->opts.mixed >= 0;
   int rc = h->mixed ? upload_levels<float>(h, hier, h->lv32, true) : CS_B200_OK;
   if (rc) return rc;
+  tick("levels: windows + upload");
   if (h->mixed) {
     // the fp64 side only needs level 0's omega / dinv (already on the handle)
     h->lv.resize(nl);
@@ -396,9 +413,11 @@ int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std:
       h_vals = v_local.data();
     }
   }
+  Tick tick;
   if (want_win) {
     int rc = build_windowed<T>(h, h->A0, h_rowptr.data(), h_colidx->data(), h->n_pad, (const T*)h->d_dinv);
     if (rc) return rc;
+    tick("finest operator: windows");
   }
   if (want_amg) {
     int rc = setup_amg<T>(h, h_rowptr, *h_colidx, h_vals);
