@@ -19,6 +19,7 @@
 #include "amg_host.hpp"
 #include "win_host.hpp"
 #include "kernels.cuh"
+#include "raster_assembly.cuh"
 
 using namespace csb;
 
@@ -506,15 +507,17 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
       constexpr int SMEM = WinSmem2<T, KT, MODE, true>::TOTAL;
       constexpr int SB = WinMap<T, KT, true>::SB;
       const int wg = std::max(1, std::min(h->num_sms, (m.win_nblocks + SB - 1) / SB));
-      static bool once = false;
-      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
+      static bool once[64] = {};   // per device: the attribute lives in the device's context
+      bool& set = once[h->device & 63];
+      if (!set) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); set = true; }
       k_spmm_win<T, KT, MODE, true><<<wg, WTT, SMEM, h->stream>>>(w, X, Y, ep);
     } else {
       constexpr int SMEM = WinSmem2<T, KT, MODE, false>::TOTAL;
       constexpr int SB = WinMap<T, KT, false>::SB;
       const int wg = std::max(1, std::min(h->num_sms, (m.win_nblocks + SB - 1) / SB));
-      static bool once = false;
-      if (!once) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); once = true; }
+      static bool once[64] = {};
+      bool& set = once[h->device & 63];
+      if (!set) { cudaFuncSetAttribute(k_spmm_win<T, KT, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); set = true; }
       k_spmm_win<T, KT, MODE, false><<<wg, WTT, SMEM, h->stream>>>(w, X, Y, ep);
     }
   } else if (m.lpr == 4 && KT * 4 <= 32) {
@@ -1163,6 +1166,62 @@ int ensure_flush(cs_b200_handle* h) {
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
+namespace {
+template <typename T>
+int assemble_raster(cs_b200_handle* h, int64_t nrows, int64_t ncols, const T* g_host,
+                           int four, int avg_res, std::vector<int>& rp_host) {
+  const int64_t ncell = nrows * ncols;
+  T* d_g = nullptr;
+  int *d_valid = nullptr, *d_nodeid = nullptr, *d_rowcnt = nullptr;
+  auto cleanup = [&]() { cudaFree(d_g); cudaFree(d_valid); cudaFree(d_nodeid); cudaFree(d_rowcnt); };
+#define CKR(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      cleanup();                                                                           \
+      return set_err(h, CS_B200_ERR_CUDA, "CUDA error %s at %s:%d (%s)",                   \
+                     cudaGetErrorString(_e), __FILE__, __LINE__, #call);                   \
+    }                                                                                      \
+  } while (0)
+  CKR(cudaMalloc(&d_g, (size_t)ncell * sizeof(T)));
+  CKR(cudaMalloc(&d_valid, (size_t)ncell * sizeof(int)));
+  CKR(cudaMalloc(&d_nodeid, (size_t)ncell * sizeof(int)));
+  CKR(h2d(h, d_g, g_host, (size_t)ncell * sizeof(T)));
+  const int grid = (int)std::min<int64_t>((ncell + 255) / 256, (int64_t)h->num_sms * 32);
+  ras::k_valid<T><<<grid, 256, 0, h->stream>>>(ncell, d_g, d_valid);
+  CKR(cudaGetLastError());
+  CKR(ras::exclusive_scan(d_valid, d_nodeid, ncell, h->stream));
+  int last_id = 0, last_valid = 0;
+  CKR(cudaMemcpy(&last_id, d_nodeid + (ncell - 1), sizeof(int), cudaMemcpyDeviceToHost));
+  CKR(cudaMemcpy(&last_valid, d_valid + (ncell - 1), sizeof(int), cudaMemcpyDeviceToHost));
+  const int64_t n = (int64_t)last_id + last_valid;
+  if (n <= 0) { cleanup(); return set_err(h, CS_B200_ERR_ARG, "raster has no cell with conductance > 0"); }
+  CKR(cudaMalloc(&d_rowcnt, (size_t)(n + 1) * sizeof(int)));
+  CKR(cudaMemsetAsync(d_rowcnt, 0, (size_t)(n + 1) * sizeof(int), h->stream));
+  ras::k_count<<<grid, 256, 0, h->stream>>>((int)nrows, (int)ncols, four, d_valid, d_nodeid, d_rowcnt);
+  CKR(cudaGetLastError());
+  CKR(cudaMalloc(&h->d_rowptr, (size_t)(n + 1) * sizeof(int)));
+  CKR(ras::exclusive_scan(d_rowcnt, h->d_rowptr, n + 1, h->stream));
+  rp_host.resize((size_t)n + 1);
+  CKR(cudaMemcpy(rp_host.data(), h->d_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  const int64_t nnz = rp_host[(size_t)n];
+  if (nnz <= 0) { cleanup(); return set_err(h, CS_B200_ERR_ARG, "assembled matrix is empty"); }
+  CKR(cudaMalloc(&h->d_colidx, (size_t)nnz * sizeof(int)));
+  CKR(cudaMalloc(&h->d_vals, (size_t)nnz * sizeof(T)));
+  ras::k_fill<T><<<grid, 256, 0, h->stream>>>((int)nrows, (int)ncols, four, avg_res, d_g, d_valid, d_nodeid,
+                                              h->d_rowptr, h->d_colidx, (T*)h->d_vals);
+  CKR(cudaGetLastError());
+  CKR(cudaStreamSynchronize(h->stream));
+#undef CKR
+  cleanup();
+  h->n = n;
+  h->nnz = nnz;
+  h->n_pad = (n + 3) / 4 * 4;
+  return CS_B200_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int cs_b200_version(void) { return 1001; }
@@ -1262,6 +1321,57 @@ int cs_b200_create_from_device(int64_t n, int64_t nnz, const int32_t* d_rowptr,
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->stats.setup_ms = ms;
   *out = h;
+  return CS_B200_OK;
+}
+
+int cs_b200_create_from_raster(int64_t nrows, int64_t ncols, const void* g, int dtype,
+                               int four_neighbors, int avg_res, int device,
+                               const cs_b200_opts* opts, cs_b200_handle** out,
+                               int64_t* n_out, int64_t* nnz_out) {
+  if (!out) return set_err(nullptr, CS_B200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (nrows <= 0 || ncols <= 0 || !g || (dtype != CS_B200_F32 && dtype != CS_B200_F64) ||
+      nrows > (int64_t)1 << 30 || ncols > (int64_t)1 << 30 || nrows * ncols >= (int64_t)1 << 31)
+    return set_err(nullptr, CS_B200_ERR_ARG, "bad arguments");
+  cs_b200_handle* h = new cs_b200_handle();
+  h->n = 0; h->nnz = 0; h->dtype = dtype; h->device = device;
+  h->owns_matrix = true;
+  int rc = common_create(h, opts);
+  if (rc) { g_create_error = h->err; cs_b200_destroy(h); return rc; }
+  cudaEventRecord(h->ev0, h->stream);
+  std::vector<int> rp;
+  rc = dtype == CS_B200_F64
+           ? assemble_raster<double>(h, nrows, ncols, (const double*)g, four_neighbors ? 1 : 0, avg_res ? 1 : 0, rp)
+           : assemble_raster<float>(h, nrows, ncols, (const float*)g, four_neighbors ? 1 : 0, avg_res ? 1 : 0, rp);
+  if (!rc)
+    rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, nullptr, (const double*)nullptr)
+                              : finish_setup<float>(h, rp, nullptr, (const float*)nullptr);
+  if (rc) { g_create_error = h->err; cs_b200_destroy(h); return rc; }
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.setup_ms = ms;
+  if (n_out) *n_out = h->n;
+  if (nnz_out) *nnz_out = h->nnz;
+  *out = h;
+  return CS_B200_OK;
+}
+
+int cs_b200_get_csr(cs_b200_handle* h, int32_t* rowptr, int32_t* colidx, void* vals) {
+  if (!h) return CS_B200_ERR_ARG;
+  cudaSetDevice(h->device);
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (rowptr) CK(h, cudaMemcpy(rowptr, h->d_rowptr, (size_t)(h->n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  if (colidx) CK(h, cudaMemcpy(colidx, h->d_colidx, (size_t)h->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+  if (vals) CK(h, cudaMemcpy(vals, h->d_vals, (size_t)h->nnz * h->esize(), cudaMemcpyDeviceToHost));
+  return CS_B200_OK;
+}
+
+int cs_b200_get_dims(const cs_b200_handle* h, int64_t* n, int64_t* nnz) {
+  if (!h) return CS_B200_ERR_ARG;
+  if (n) *n = h->n;
+  if (nnz) *nnz = h->nnz;
   return CS_B200_OK;
 }
 

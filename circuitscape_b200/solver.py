@@ -85,6 +85,14 @@ class B200Factor:
         bits = 64 if rowptr.dtype == np.int64 else 32
         if colidx.dtype != rowptr.dtype:
             colidx = colidx.astype(rowptr.dtype)
+        opts = self._opts(solver, log_transform)
+        rc = lib.cs_b200_create(self.n, m.nnz, _lib._ptr(rowptr), _lib._ptr(colidx), _lib._ptr(vals),
+                                bits, 0, _lib.dtype_code(self.dtype), solver.device,
+                                C.byref(opts), C.byref(self._h))
+        _lib.check(lib, None, rc)
+
+    @staticmethod
+    def _opts(solver, log_transform=False):
         opts = _lib.Opts()
         opts.precond = _lib.PRECOND_AMG if solver.precond == "amg" else _lib.PRECOND_JACOBI
         opts.panel_width = solver.panel_width
@@ -93,10 +101,42 @@ class B200Factor:
         opts.log_transform = 1 if log_transform else 0
         opts.window = {"auto": 0, "on": 1, "off": -1}[solver.window]
         opts.mixed = 0 if solver.mixed else -1
-        rc = lib.cs_b200_create(self.n, m.nnz, _lib._ptr(rowptr), _lib._ptr(colidx), _lib._ptr(vals),
-                                bits, 0, _lib.dtype_code(self.dtype), solver.device,
-                                C.byref(opts), C.byref(self._h))
+        return opts
+
+    @classmethod
+    def from_raster(cls, conductance, solver: "CUDASolver", four_neighbors=False, avg_res=False,
+                    log_transform=False):
+        """Factor of a whole conductance raster, assembled ON THE DEVICE
+        (cs_b200_create_from_raster): construct_node_map without polygons + construct_graph +
+        laplacian! (src/raster/pairwise.jl:271-367, src/core.jl:608-624).  `conductance`:
+        2-D array, cells <= 0 / NODATA are not nodes; rows of the factor are the reference's
+        node numbers minus one (column-major over the valid cells)."""
+        lib = _lib.load()
+        f = cls.__new__(cls)
+        f._lib = lib
+        f._h = C.c_void_p()
+        f.io_dtype = np.dtype(solver.dtype)
+        f.dtype = np.dtype(solver.device_dtype)
+        f.solver = solver
+        g = np.asfortranarray(conductance, dtype=f.dtype)       # Julia's memory order
+        n, nnz = C.c_int64(), C.c_int64()
+        opts = cls._opts(solver, log_transform)
+        rc = lib.cs_b200_create_from_raster(g.shape[0], g.shape[1], _lib._ptr(g), _lib.dtype_code(f.dtype),
+                                            1 if four_neighbors else 0, 1 if avg_res else 0, solver.device,
+                                            C.byref(opts), C.byref(f._h), C.byref(n), C.byref(nnz))
         _lib.check(lib, None, rc)
+        f.n = n.value
+        return f
+
+    def get_csr(self):
+        """The handle's operator as a SciPy CSR (downloaded; parity / debugging hook)."""
+        n, nnz = C.c_int64(), C.c_int64()
+        _lib.check(self._lib, self._h, self._lib.cs_b200_get_dims(self._h, C.byref(n), C.byref(nnz)))
+        rp = np.empty(n.value + 1, dtype=np.int32)
+        ci = np.empty(nnz.value, dtype=np.int32)
+        va = np.empty(nnz.value, dtype=self.dtype)
+        _lib.check(self._lib, self._h, self._lib.cs_b200_get_csr(self._h, _lib._ptr(rp), _lib._ptr(ci), _lib._ptr(va)))
+        return sp.csr_matrix((va, ci, rp), shape=(n.value, n.value))
 
     # -- lifetime ---------------------------------------------------------
     def close(self):

@@ -103,6 +103,30 @@ int cs_b200_create_from_device(int64_t n, int64_t nnz, const int32_t* d_rowptr,
                                const int32_t* d_colidx, const void* d_vals, int dtype,
                                int device, const cs_b200_opts* opts, cs_b200_handle** out);
 
+/* The step BEFORE the path: assemble the Laplacian of a conductance raster
+ * on the device and build the handle on it -- construct_node_map without polygons
+ * (src/raster/pairwise.jl:271-281), construct_graph (src/raster/pairwise.jl:317-367) and
+ * laplacian! (src/core.jl:608-624) as three kernels around two prefix sums; nothing of size nnz
+ * is built on the host or crosses PCIe on the way in.
+ * g: host, COLUMN-major nrows x ncols (a Julia Matrix as it lies in memory), element type `dtype`;
+ * cells with g <= 0 (0, NODATA -9999, NaN) are not nodes.  Nodes are numbered 0.. in memory
+ * order over the valid cells -- the reference's numbering minus one.  avg_res / four_neighbors:
+ * connect_using_avg_resistances / connect_four_neighbors_only.  The whole raster becomes ONE
+ * operator (block diagonal over its connected components; a solve's sources and ground must
+ * lie in one component, as they do in the reference's per-component calls).
+ * *n_out / *nnz_out (optional): nodes and stored entries of the assembled matrix.            */
+int cs_b200_create_from_raster(int64_t nrows, int64_t ncols, const void* g, int dtype,
+                               int four_neighbors, int avg_res, int device,
+                               const cs_b200_opts* opts, cs_b200_handle** out,
+                               int64_t* n_out, int64_t* nnz_out);
+
+/* Copy the handle's CSR (0-based, int32 indices, values of the handle's dtype) to host buffers
+ * of n+1, nnz and nnz elements; any pointer may be NULL.  Parity / debugging hook.            */
+int cs_b200_get_csr(cs_b200_handle* h, int32_t* rowptr, int32_t* colidx, void* vals);
+
+/* n and nnz of the handle's operator. */
+int cs_b200_get_dims(const cs_b200_handle* h, int64_t* n, int64_t* nnz);
+
 void cs_b200_destroy(cs_b200_handle* h);
 
 /* Text of the last error on this handle (or of the last failed create if h==NULL). */

@@ -12,12 +12,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--what", default="raster", choices=["raster", "network"])
 ap.add_argument("--rows", type=int, default=4000)
 ap.add_argument("--pairs", type=int, default=16)
+ap.add_argument("--device-assembly", action="store_true",
+                help="also build the handle with cs_b200_create_from_raster (Laplacian assembled on the GPU) and compare")
 ap.add_argument("--precisions", default="double", help="comma list of double,single (single = fp32 host buffers, fp64 on device)")
 a = ap.parse_args()
 
 if a.what == "raster":
     t = time.time()
-    L, _ = graph.synthetic_raster_laplacian(a.rows, a.rows, seed=42)
+    L, g = graph.synthetic_raster_laplacian(a.rows, a.rows, seed=42)
     n = L.shape[0]
     print(f"assembled {a.rows}^2: n={n} nnz={L.nnz} in {time.time()-t:.1f}s", flush=True)
     nodes = graph.focal_nodes(n, 8, seed=7)
@@ -40,5 +42,12 @@ if a.what == "raster":
                   f"max rel dev of R from fp64 {np.abs(R-ref).max()/ref.max():.2e}; launches {st['kernel_launches']}", flush=True)
             for k in (1, 8):
                 print(f"   spmm k={k}: {f.bench_spmm(k, reps=10, flush_l2=True):.3f} ms   cg_iter: {f.bench_cg_iter(k, reps=10):.3f} ms", flush=True)
+    if a.device_assembly:
+        t = time.time()
+        with cb.B200Factor.from_raster(g, cb.CUDASolver()) as f:
+            ts = time.time() - t
+            o = f.solve_pairs(src, dst, accumulate=True)
+            print(f"device assembly: handle from the {a.rows}^2 conductance raster in {ts:.1f}s (n={f.n}); "
+                  f"max rel dev of R from the host-assembled run {np.abs(o['R'] - ref).max() / ref.max():.2e}", flush=True)
 else:
     raise SystemExit("network configuration: use profiles/run_network.py")

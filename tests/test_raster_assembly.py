@@ -1,0 +1,158 @@
+"""On-device raster assembly (circuitscape_b200/csrc/raster_assembly.cuh).
+
+CPU: the kernels' index walk restated in Python (same slot order, same diagonal placement)
+against the host assembly the rest of the suite uses -- pins the algorithm.
+GPU: the CSR the device builds, downloaded through cs_b200_get_csr, against the same host
+assembly, and a solve on the device-assembled handle against the host-assembled one."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import circuitscape_b200 as cb
+from circuitscape_b200 import graph
+
+
+def host_laplacian(g, four, avg_res):
+    nodemap = graph.construct_node_map(g, None)
+    return graph.laplacian(graph.construct_graph(g, nodemap, avg_res, four)), nodemap
+
+
+def emulate_device_walk(g, four, avg_res):
+    """k_valid / scan / k_count / scan / k_fill of raster_assembly.cuh, one 'thread' per cell."""
+    nrows, ncols = g.shape
+    gf = np.asfortranarray(g).ravel(order="F")             # cell index = r + c * nrows
+    valid = (gf > 0).astype(np.int64)
+    nodeid = np.cumsum(valid) - valid
+    n = int(nodeid[-1] + valid[-1])
+    s2 = 1.4142135623730951
+
+    def weight(a, b, diagonal):
+        if avg_res:
+            return 1.0 / (s2 * (1.0 / a + 1.0 / b) / 2.0) if diagonal else 1.0 / ((1.0 / a + 1.0 / b) / 2.0)
+        return (a + b) / (2.0 * s2) if diagonal else (a + b) / 2.0
+
+    rowcnt = np.zeros(n + 1, dtype=np.int64)
+    for i in range(nrows * ncols):
+        if not valid[i]:
+            continue
+        r, c = i % nrows, i // nrows
+        cnt = 1
+        for k in range(9):
+            if k == 4:
+                continue
+            dr, dc = k % 3 - 1, k // 3 - 1
+            if four and dr != 0 and dc != 0:
+                continue
+            rr, cc = r + dr, c + dc
+            if rr < 0 or rr >= nrows or cc < 0 or cc >= ncols:
+                continue
+            cnt += valid[cc * nrows + rr]
+        rowcnt[nodeid[i]] = cnt
+    rowptr = np.cumsum(rowcnt) - rowcnt
+    nnz = int(rowptr[n])
+    colidx = np.full(nnz, -1, dtype=np.int64)
+    vals = np.zeros(nnz)
+    for i in range(nrows * ncols):
+        if not valid[i]:
+            continue
+        r, c = i % nrows, i // nrows
+        p = rowptr[nodeid[i]]
+        deg = 0.0
+        diag_pos = p
+        for k in range(9):
+            if k == 4:
+                diag_pos = p
+                p += 1
+                continue
+            dr, dc = k % 3 - 1, k // 3 - 1
+            diagonal = dr != 0 and dc != 0
+            if four and diagonal:
+                continue
+            rr, cc = r + dr, c + dc
+            if rr < 0 or rr >= nrows or cc < 0 or cc >= ncols:
+                continue
+            j = cc * nrows + rr
+            if not valid[j]:
+                continue
+            w = weight(gf[i], gf[j], diagonal)
+            colidx[p] = nodeid[j]
+            vals[p] = -w
+            deg += w
+            p += 1
+        colidx[diag_pos] = nodeid[i]
+        vals[diag_pos] = deg
+    return sp.csr_matrix((vals, colidx, rowptr[: n + 1]), shape=(n, n))
+
+
+def rasters():
+    rng = np.random.default_rng(4)
+    full = rng.uniform(0.2, 3.0, (9, 7))
+    holes = rng.uniform(0.2, 3.0, (13, 11))
+    holes[rng.random(holes.shape) < 0.25] = 0.0
+    holes[0, 0] = -9999.0
+    holes[5, 5] = np.nan
+    thin = rng.uniform(0.5, 1.5, (1, 6))
+    return {"full": full, "holes": holes, "thin": thin}
+
+
+@pytest.mark.parametrize("four", [False, True])
+@pytest.mark.parametrize("avg_res", [False, True])
+@pytest.mark.parametrize("name", ["full", "holes", "thin"])
+def test_device_walk_restated_on_cpu(name, four, avg_res):
+    g = rasters()[name]
+    gh = np.where(np.isnan(g) | (g <= 0), 0.0, g)
+    L, _ = host_laplacian(gh, four, avg_res)
+    E = emulate_device_walk(np.where(np.isnan(g), np.nan, g), four, avg_res)
+    assert E.shape == L.shape
+    E.sort_indices()
+    # the device keeps explicit zeros nowhere and stores every diagonal (also 0 for isolated cells)
+    D = (E - L).tocsr()
+    assert np.abs(D.data).max(initial=0.0) < 1e-14 * np.abs(L.data).max()
+    assert np.all(np.diff(E.indices)[np.diff(np.repeat(np.arange(E.shape[0]), np.diff(E.indptr))) == 0] > 0), \
+        "column indices ascending within a row"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("four", [False, True])
+@pytest.mark.parametrize("avg_res", [False, True])
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_device_assembly_matches_host(four, avg_res, precision):
+    rng = np.random.default_rng(8)
+    g = rng.uniform(0.2, 3.0, (157, 93))
+    g[rng.random(g.shape) < 0.12] = 0.0
+    g[3, 4] = -9999.0
+    L, nodemap = host_laplacian(np.where(g > 0, g, 0.0), four, avg_res)
+    solver = cb.CUDASolver(precision=precision, f32_compute=(precision == "single"), precond="jacobi")
+    with cb.B200Factor.from_raster(g, solver, four_neighbors=four, avg_res=avg_res) as f:
+        A = f.get_csr()
+        assert f.n == L.shape[0] == int(nodemap.max())
+    assert A.shape == L.shape
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    assert np.all(np.diff(A.indices)[np.diff(rows) == 0] > 0), "device column indices ascending within a row"
+    assert np.all(np.diff(A.indptr) >= 1), "every node stores its diagonal"
+    tol = 1e-14 if precision == "double" else 1e-6
+    D = (A.astype(np.float64) - L).tocsr()
+    assert np.abs(D.data).max(initial=0.0) <= tol * np.abs(L.data).max()
+    A64 = A.astype(np.float64); A64.eliminate_zeros()
+    L0 = L.copy(); L0.eliminate_zeros()
+    assert A64.nnz == L0.nnz
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precond", ["jacobi", "amg"])
+def test_solve_on_device_assembled_raster(precond):
+    """pairs solved on the device-assembled operator == pairs solved on the uploaded one"""
+    rng = np.random.default_rng(9)
+    g = rng.uniform(1.0, 10.0, (220, 180))
+    g = 1.0 / g
+    L, nodemap = host_laplacian(g, False, False)
+    nodes = graph.focal_nodes(L.shape[0], 5, seed=7)
+    src, dst = graph.all_pairs(nodes)
+    with cb.B200Factor(L, cb.CUDASolver(precond=precond)) as f0:
+        r0 = f0.solve_pairs(src, dst, accumulate=True)
+        c0, m0 = f0.read_currents()
+    with cb.B200Factor.from_raster(g, cb.CUDASolver(precond=precond)) as f1:
+        r1 = f1.solve_pairs(src, dst, accumulate=True)
+        c1, m1 = f1.read_currents()
+    assert np.abs(r1["R"] - r0["R"]).max() <= 1e-9 * np.abs(r0["R"]).max()
+    assert np.abs(c1 - c0).max() <= 1e-8 * np.abs(c0).max()
