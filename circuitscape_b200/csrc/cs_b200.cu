@@ -1331,8 +1331,10 @@ int cs_b200_create_from_raster(int64_t nrows, int64_t ncols, const void* g, int 
   if (!out) return set_err(nullptr, CS_B200_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (nrows <= 0 || ncols <= 0 || !g || (dtype != CS_B200_F32 && dtype != CS_B200_F64) ||
-      nrows > (int64_t)1 << 30 || ncols > (int64_t)1 << 30 || nrows * ncols >= (int64_t)1 << 31)
+      nrows > (int64_t)1 << 30 || ncols > (int64_t)1 << 30)
     return set_err(nullptr, CS_B200_ERR_ARG, "bad arguments");
+  if (nrows * ncols * 9 >= (int64_t)1 << 31)
+    return set_err(nullptr, CS_B200_ERR_UNSUPPORTED, "raster too large: 9 * cells must be < 2^31 (device indices are int32)");
   cs_b200_handle* h = new cs_b200_handle();
   h->n = 0; h->nnz = 0; h->dtype = dtype; h->device = device;
   h->owns_matrix = true;
