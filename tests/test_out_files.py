@@ -1,0 +1,104 @@
+"""Output stage (circuitscape_b200/out.py): files written from the host driver's results are
+read back and compared with the reference's golden files under the reference's own tolerances
+(test/test_utils.jl:144-163, 196, 217-226).  CPU only (FakeFactor stands in for the device)."""
+import os
+
+import numpy as np
+import pytest
+
+import circuitscape_b200 as cb
+from circuitscape_b200 import out as O
+from circuitscape_b200 import solver as S
+from oracle import circuitscape_oracle as co
+
+from . import cases
+from .fake_factor import FakeFactor
+
+TOL = 1e-6
+
+
+@pytest.fixture(autouse=True)
+def fake_device(monkeypatch):
+    monkeypatch.setattr(S, "construct_cholesky_factor", lambda m, s, **kw: FakeFactor(m, s, **kw))
+    monkeypatch.setattr(S, "multiple_solve", lambda s, m, b: FakeFactor(m, s).solve_rhs(np.asarray(b))[0])
+
+
+def read_asc(path):
+    with open(path) as f:
+        hdr = {}
+        for _ in range(6):
+            k, v = f.readline().split()
+            hdr[k.lower()] = float(v)
+        a = np.array([[float(x) for x in ln.split()] for ln in f if ln.strip()])
+    assert a.shape == (int(hdr["nrows"]), int(hdr["ncols"]))
+    return a, hdr
+
+
+def read_table(path):
+    with open(path) as f:
+        return np.array([[float(x) for x in ln.split()] for ln in f if ln.strip()])
+
+
+@pytest.mark.parametrize("name", ["sgVerify1", "sgVerify3", "sgVerify12"])
+def test_raster_pairwise_files(golden, name, tmp_path):
+    r, exp = cases.run_raster_pairwise(golden, name, cb.CUDASolver())
+    cfg, inp, _ = co.load_case(golden, name)
+    shape = inp["habitat_file"][1].shape
+    meta = O.RasterMeta(ncols=shape[1], nrows=shape[0], xllcorner=3.5, yllcorner=-2.0, cellsize=0.25)
+    of = str(tmp_path / "out" / f"{name}.out")
+    flags = cb.Flags.from_cfg(cfg)
+    written = O.write_pairwise_outputs(r, of, meta, write_cum=True, write_max=flags.outputflags.write_max_cur_maps)
+    assert all(os.path.exists(p) for p in written)
+    pref = of[:-4]
+    res = read_table(pref + "_resistances.out")
+    assert np.all(np.abs(res - exp["resistances.out"]) <= np.sqrt(TOL))
+    c3 = read_table(pref + "_resistances_3columns.out")
+    if "resistances_3columns.out" in exp and exp["resistances_3columns.out"].shape == c3.shape:
+        assert np.all(np.abs(c3 - exp["resistances_3columns.out"]) <= np.sqrt(TOL))
+    n = 0
+    for key, gold in exp.items():
+        if not key.endswith(".asc"):
+            continue
+        path = f"{pref}_{key}"
+        if not os.path.exists(path):
+            continue                                     # stale goldens the current reference does not write
+        a, hdr = read_asc(path)
+        assert hdr["nodata_value"] == -9999 and hdr["cellsize"] == 0.25 and hdr["xllcorner"] == 3.5
+        assert np.sum((a - gold) ** 2) < TOL
+        n += 1
+    assert n >= 1
+
+
+def test_network_pairwise_files(golden, tmp_path):
+    prob, flags, exp = cases.network_pairwise_problem(golden, "sgNetworkVerify1", cb.CUDASolver())
+    r = cb.single_ground_all_pairs(prob, flags)
+    of = str(tmp_path / "net.out")
+    O.write_pairwise_outputs(r, of, None)
+    pref = of[:-4]
+    res = read_table(pref + "_resistances.out")
+    x = exp["resistances.out"]
+    assert np.all(np.abs(x[1:, 1:] - res[1:, 1:]) <= np.sqrt(TOL))
+    (a, b) = next(iter(r.curmaps))
+    nodes = read_table(f"{pref}_node_currents_{a}_{b}.txt")
+    v = exp[f"node_currents_{a - 1}_{b - 1}.txt"].copy(); v[:, 0] += 1
+    assert np.sum((cases.sorted_rows(nodes) - cases.sorted_rows(v)) ** 2) < TOL
+    br = read_table(f"{pref}_branch_currents_{a}_{b}.txt")
+    v = exp[f"branch_currents_{a - 1}_{b - 1}.txt"].copy(); v[:, :2] += 1
+    assert br.shape == v.shape                          # rows within 1e-6 of zero are dropped, as in the reference
+    assert np.sum((cases.sorted_rows(br) - cases.sorted_rows(v)) ** 2) < TOL
+    if r.voltmaps:
+        assert os.path.exists(f"{pref}_voltages_{a}_{b}.txt")
+
+
+def test_grid_names_and_number_format(tmp_path):
+    assert O.grid_filename("x/y.out", "_1_2").endswith("x/y_curmap_1_2.asc")
+    assert O.grid_filename("x/y.out", "", cum=True, maxmap=True).endswith("y_cum_curmap.asc")
+    assert O.grid_filename("x/y.out", "", maxmap=True, voltage=True).endswith("y_max_curmap.asc")
+    assert O.grid_filename("x/y.out", "_3", voltage=True).endswith("y_voltmap_3.asc")
+    m = O.RasterMeta(ncols=3, nrows=2)
+    a = np.array([[0.1, -9999.0, 3.0], [1e-17, 2.5e10, 7.0]])
+    p = O.write_asc(str(tmp_path / "g.asc"), a, m)
+    b, _ = read_asc(p)
+    assert np.array_equal(a, b)                         # repr-exact floats survive the round trip
+    with pytest.raises(ValueError):
+        O.write_asc(str(tmp_path / "h.asc"), a.T, m)
