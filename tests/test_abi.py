@@ -57,3 +57,15 @@ def test_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(cb.B200Unavailable):
         cb.B200Factor(sp.identity(4, format="csr"), cb.CUDASolver())
+    with pytest.raises(cb.B200Unavailable):
+        cb.B200Factor.from_raster(np.ones((3, 3)), cb.CUDASolver())
+
+
+def test_from_raster_rejects_bad_arguments_without_a_device():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    g = np.ones((2, 2))
+    rc = lib.cs_b200_create_from_raster(0, 2, g.ctypes.data, 1, 0, 0, 0, None, ctypes.byref(h), None, None)
+    assert rc == _lib.ERR_ARG
+    rc = lib.cs_b200_create_from_raster(20000, 20000, g.ctypes.data, 1, 0, 0, 0, None, ctypes.byref(h), None, None)
+    assert rc != 0 and b"too large" in lib.cs_b200_last_error(None)
