@@ -221,10 +221,22 @@ def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=
         local_nodemap = construct_local_node_map(prob.nodemap, comp, prob.polymap) if raster and not shortcut else None
         with S.construct_cholesky_factor(matrix, solver, log_transform=o.log_transform_maps) as factor:
             bs = max(1, int(solver.bs))
-            for st in range(0, len(solves), bs):                                # src/core.jl:448-452
-                sl = slice(st, min(st + bs, len(solves)))
-                res = factor.solve_pairs(src[sl], dst[sl], weight[sl], want_volt=per_pair_volt,
-                                         want_curr=per_pair_curr, accumulate=need_curr)
+
+            def batches():
+                if getattr(solver, "superpose", False) and not shortcut and len(solves) > 1:
+                    # one solve per focal NODE of the component, every pair by superposition
+                    # (the Shortcut algebra of src/core.jl:685-739 applied to the voltages)
+                    nodes, inv = np.unique(np.concatenate([src, dst]), return_inverse=True)
+                    yield slice(0, len(solves)), factor.solve_pairs_superposed(
+                        nodes, inv[:len(src)], inv[len(src):], weight, want_volt=per_pair_volt,
+                        want_curr=per_pair_curr, accumulate=need_curr)
+                    return
+                for st in range(0, len(solves), bs):                            # src/core.jl:448-452
+                    sl = slice(st, min(st + bs, len(solves)))
+                    yield sl, factor.solve_pairs(src[sl], dst[sl], weight[sl], want_volt=per_pair_volt,
+                                                 want_curr=per_pair_curr, accumulate=need_curr)
+
+            for sl, res in batches():
                 out.stats.append(factor.stats())
                 out.num_solves += len(res["R"])
                 out.iterations += int(res["iters"].sum())

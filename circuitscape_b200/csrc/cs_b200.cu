@@ -979,6 +979,115 @@ int solve_sources_t(cs_b200_handle* h, int64_t k, const int64_t* colptr, const i
                     int64_t itmax, int64_t nprobe, const int64_t* probe, T* probe_volt, T* volt,
                     T* curr, int accumulate, int64_t* iters, double* relres);
 
+// ---- superposition driver (cs_b200_solve_pairs_superposed) ----------------------------------
+// panel of point solves  A u_x = e_{nodes[x]} - e_{nodes[0]}  for x = x0 .. x0+KT-1 (1-based among
+// the focal nodes); the shifted solutions land in columns x0-1 .. of U (column-major, ld = n_pad)
+template <typename T, int KT>
+int point_panel(cs_b200_handle* h, int64_t x0, const int64_t* nodes, double rtol, int64_t itmax, T* U,
+                int64_t* point_iters, bool* any_fail, bool* any_maxit, std::string* msg) {
+  const size_t nelem = (size_t)h->n_pad * KT;
+  PanelCtl* hc = h->h_ctl;
+  std::memset(hc, 0, sizeof(PanelCtl));
+  for (int c = 0; c < KT; ++c) {
+    hc->src[c] = nodes[0];
+    hc->dst[c] = nodes[x0 + c];
+    hc->weight[c] = 1.0;
+  }
+  CK(h, cudaMemcpyAsync(h->d_ctl, hc, sizeof(PanelCtl), cudaMemcpyHostToDevice, h->stream));
+  h->stats.h2d_bytes += sizeof(PanelCtl);
+  CK(h, cudaMemsetAsync(h->B, 0, nelem * sizeof(T), h->stream));
+  k_pair_rhs<T, KT><<<1, 32, 0, h->stream>>>((T*)h->B, h->d_ctl);
+  h->stats.kernel_launches++;
+  int rc = solve_panel<T, KT>(h, rtol, itmax);
+  if (rc) return rc;
+  gather_panel_status(h, KT, 0, nullptr, nullptr, itmax, any_fail, any_maxit, msg);
+  if (point_iters)
+    for (int c = 0; c < KT; ++c) point_iters[x0 - 1 + c] = h->h_ctl->iters[c];
+  k_pair_extract<T, KT><<<1, 32, 0, h->stream>>>((const T*)h->X, h->d_ctl);
+  const int tg = (int)std::min<size_t>(4096, (nelem + 255) / 256);
+  k_panel_to_cm<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n_pad, (const T*)h->X,
+                                                  U + (size_t)(x0 - 1) * h->n_pad, h->d_ctl, 1);
+  h->stats.kernel_launches += 2;
+  CK(h, cudaGetLastError());
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CS_B200_OK;
+}
+
+// panel of pairs c0 .. c0+KT-1 formed from U; same outputs as pairs_panel
+template <typename T, int KT>
+int combine_panel(cs_b200_handle* h, int64_t c0, const int64_t* nodes, const int64_t* pi, const int64_t* pj,
+                  const double* weight, const T* U, int* d_ci, int* d_cj, T* R, T* volt, T* curr,
+                  int accumulate, double* relres, int64_t itmax, bool* any_fail, bool* any_maxit,
+                  std::string* msg) {
+  const size_t nelem = (size_t)h->n_pad * KT;
+  PanelCtl* hc = h->h_ctl;
+  std::memset(hc, 0, sizeof(PanelCtl));
+  int ci[MAXKT], cj[MAXKT];
+  for (int c = 0; c < KT; ++c) {
+    hc->src[c] = nodes[pi[c0 + c]];
+    hc->dst[c] = nodes[pj[c0 + c]];
+    hc->weight[c] = weight ? weight[c0 + c] : 1.0;
+    ci[c] = (int)pi[c0 + c] - 1;      // point 0 is the reference: its solution is identically 0
+    cj[c] = (int)pj[c0 + c] - 1;
+  }
+  CK(h, cudaMemcpyAsync(h->d_ctl, hc, sizeof(PanelCtl), cudaMemcpyHostToDevice, h->stream));
+  CK(h, h2d(h, d_ci, ci, KT * sizeof(int)));
+  CK(h, h2d(h, d_cj, cj, KT * sizeof(int)));
+  h->stats.h2d_bytes += sizeof(PanelCtl) + 2.0 * KT * sizeof(int);
+  const int tg = (int)std::min<size_t>(4096, (nelem + 255) / 256);
+  k_combine<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n_pad, U, d_ci, d_cj, (T*)h->X);
+  CK(h, cudaMemsetAsync(h->B, 0, nelem * sizeof(T), h->stream));
+  k_pair_rhs<T, KT><<<1, 32, 0, h->stream>>>((T*)h->B, h->d_ctl);
+  // the reference's gate on the combined voltage: AP = B - A X, ||AP|| / ||B||  (core.jl:640-641)
+  launch_spmm<T, KT, SP_RESNORM>(h, (const T*)h->X, (T*)h->AP, (const T*)h->B);
+  h->stats.kernel_launches += 2;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PanelCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  gather_panel_status(h, KT, c0, nullptr, relres, itmax, any_fail, any_maxit, msg);
+  k_pair_extract<T, KT><<<1, 32, 0, h->stream>>>((const T*)h->X, h->d_ctl);
+  h->stats.kernel_launches++;
+  if (accumulate || curr) {
+    const int grid = (int)std::min<int64_t>(h->grid_spmm, (h->n + (NT / KT) - 1) / (NT / KT));
+    k_cur_max<T, KT><<<grid, NT, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx,
+                                                 (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
+                                                 h->d_partials);
+    k_cur_acc<T, KT><<<grid, NT, 0, h->stream>>>(
+        (int)h->n, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
+        curr ? (T*)h->AP : nullptr, (T*)h->d_cum, (T*)h->d_max, accumulate,
+        h->opts.log_transform, KT);
+    h->stats.kernel_launches += 2;
+  }
+  CK(h, cudaGetLastError());
+  if (curr) {
+    k_panel_to_cm<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->AP,
+                                                    (T*)h->stage, h->d_ctl, 0);
+    h->stats.kernel_launches++;
+    CK(h, cudaMemcpyAsync(curr + (size_t)c0 * h->n, h->stage, (size_t)h->n * KT * sizeof(T),
+                          cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (double)h->n * KT * sizeof(T);
+  }
+  if (volt) {
+    k_panel_to_cm<T, KT><<<tg, 256, 0, h->stream>>>((int)h->n, (size_t)h->n, (const T*)h->X,
+                                                    (T*)h->stage, h->d_ctl, 1);
+    h->stats.kernel_launches++;
+    CK(h, cudaMemcpyAsync(volt + (size_t)c0 * h->n, h->stage, (size_t)h->n * KT * sizeof(T),
+                          cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (double)h->n * KT * sizeof(T);
+  }
+  CK(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PanelCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->stats.d2h_bytes += sizeof(PanelCtl);
+  for (int c = 0; c < KT; ++c) R[c0 + c] = (T)(h->h_ctl->xdst[c] - h->h_ctl->xsrc[c]);
+  return CS_B200_OK;
+}
+
+template <typename T>
+int solve_pairs_superposed_t(cs_b200_handle* h, int64_t np, const int64_t* nodes, int64_t k,
+                             const int64_t* pi, const int64_t* pj, const double* weight, double rtol,
+                             int64_t itmax, T* R, T* volt, T* curr, int accumulate,
+                             int64_t* point_iters, double* relres);
+
 int ensure_io_pipeline(cs_b200_handle* h) {
   if (h->s_in) return CS_B200_OK;
   CK(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
@@ -1097,6 +1206,49 @@ int solve_sources_t(cs_b200_handle* h, int64_t k, const int64_t* colptr, const i
     if (rc) return rc;
     c0 += kt;
   }
+  if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
+  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
+  return CS_B200_OK;
+}
+
+template <typename T>
+int solve_pairs_superposed_t(cs_b200_handle* h, int64_t np, const int64_t* nodes, int64_t k,
+                             const int64_t* pi, const int64_t* pj, const double* weight, double rtol,
+                             int64_t itmax, T* R, T* volt, T* curr, int accumulate,
+                             int64_t* point_iters, double* relres) {
+  bool any_fail = false, any_maxit = false;
+  std::string msg;
+  T* U = nullptr;
+  int *d_ci = nullptr, *d_cj = nullptr;
+  const size_t ubytes = (size_t)h->n_pad * (size_t)(np - 1) * sizeof(T);
+  auto cleanup = [&]() { cudaFree(U); cudaFree(d_ci); cudaFree(d_cj); };
+  cudaError_t e = cudaMalloc(&U, ubytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_ci, MAXKT * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&d_cj, MAXKT * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(U, 0, ubytes, h->stream);
+  if (e != cudaSuccess) {
+    cleanup();
+    return set_err(h, CS_B200_ERR_CUDA, "CUDA error %s allocating %zu bytes for the point solutions",
+                   cudaGetErrorString(e), ubytes);
+  }
+  int rc = 0;
+  int64_t x0 = 1;
+  while (!rc && x0 < np) {
+    const int kt = next_kt(np - x0, h->ktmax);
+    DISPATCH_KT(kt, (rc = point_panel<T, KT>(h, x0, nodes, rtol, itmax, U, point_iters, &any_fail,
+                                             &any_maxit, &msg)));
+    x0 += kt;
+  }
+  int64_t c0 = 0;
+  while (!rc && c0 < k) {
+    const int kt = next_kt(k - c0, h->ktmax);
+    DISPATCH_KT(kt, (rc = combine_panel<T, KT>(h, c0, nodes, pi, pj, weight, U, d_ci, d_cj, R, volt, curr,
+                                               accumulate, relres, itmax, &any_fail, &any_maxit, &msg)));
+    c0 += kt;
+  }
+  cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (rc) return rc;
   if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
   if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
   return CS_B200_OK;
@@ -1679,6 +1831,31 @@ int cs_b200_solve_sources(cs_b200_handle* h, int64_t k, const int64_t* colptr, c
                : solve_sources_t<float>(h, k, colptr, rows, vals, ref, weight, rtol, itmax, nprobe, probe,
                                         (float*)probe_volt, (float*)volt, (float*)curr, accumulate, iters,
                                         relres);
+  end_call(h);
+  return rc;
+}
+
+int cs_b200_solve_pairs_superposed(cs_b200_handle* h, int64_t np, const int64_t* nodes, int64_t k,
+                                   const int64_t* pi, const int64_t* pj, const double* weight,
+                                   double rtol, int64_t itmax, void* R, void* volt, void* curr,
+                                   int accumulate, int64_t* point_iters, double* relres) {
+  if (!h || np < 2 || !nodes || k < 1 || !pi || !pj || !R || !(rtol >= 0) || itmax < 0)
+    return set_err(h, CS_B200_ERR_ARG, "bad solve_pairs_superposed arguments");
+  for (int64_t x = 0; x < np; ++x) {
+    if (nodes[x] < 0 || nodes[x] >= h->n)
+      return set_err(h, CS_B200_ERR_ARG, "focal node %lld out of range", (long long)x);
+    if (x > 0 && nodes[x] == nodes[0])
+      return set_err(h, CS_B200_ERR_ARG, "focal node %lld repeats the reference node", (long long)x);
+  }
+  for (int64_t c = 0; c < k; ++c)
+    if (pi[c] < 0 || pi[c] >= np || pj[c] < 0 || pj[c] >= np || nodes[pi[c]] == nodes[pj[c]])
+      return set_err(h, CS_B200_ERR_ARG, "pair %lld: indices out of range or equal nodes", (long long)c);
+  begin_call(h);
+  int rc = h->dtype == CS_B200_F64
+               ? solve_pairs_superposed_t<double>(h, np, nodes, k, pi, pj, weight, rtol, itmax, (double*)R,
+                                                  (double*)volt, (double*)curr, accumulate, point_iters, relres)
+               : solve_pairs_superposed_t<float>(h, np, nodes, k, pi, pj, weight, rtol, itmax, (float*)R,
+                                                 (float*)volt, (float*)curr, accumulate, point_iters, relres);
   end_call(h);
   return rc;
 }

@@ -1266,6 +1266,24 @@ __global__ void k_probe(const T* __restrict__ X, const PanelCtl* __restrict__ ct
   }
 }
 
+// superposition driver: X[:, c] = U[:, cj[c]] - U[:, ci[c]] on a panel (U column-major with
+// leading dimension n_pad; column index -1 = the reference node's identically-zero solution)
+template <typename T, int KT>
+__global__ void k_combine(int n, size_t n_pad, const T* __restrict__ U, const int* __restrict__ ci,
+                          const int* __restrict__ cj, T* __restrict__ X) {
+  const size_t total = n_pad * KT;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = e / KT;
+    const int c = (int)(e % KT);
+    T v = T(0);
+    if (i < (size_t)n) {
+      const int a = ci[c], b = cj[c];
+      v = (b >= 0 ? U[(size_t)b * n_pad + i] : T(0)) - (a >= 0 ? U[(size_t)a * n_pad + i] : T(0));
+    }
+    X[e] = v;
+  }
+}
+
 // staging (column-major n x KT, leading dimension ld) <-> panel (row-major n_pad x KT)
 template <typename T, int KT>
 __global__ void k_cm_to_panel(int n, size_t ld, const T* __restrict__ cm, T* __restrict__ panel,

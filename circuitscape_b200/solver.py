@@ -42,6 +42,7 @@ class CUDASolver:
     window: str = "auto"             # TMA-staged windowed SpMM: auto | on | off
     f32_compute: bool = False        # precision = single: keep fp32 ON THE DEVICE too (see B200Factor)
     mixed: bool = True               # fp64 + AMG: fp32 V-cycle inside fp64 CG
+    superpose: bool = False          # pairwise driver: one solve per focal NODE, pairs by superposition
 
     @property
     def dtype(self):
@@ -244,6 +245,33 @@ class B200Factor:
                                            self.solver.itmax if itmax is None else itmax,
                                            _lib._ptr(R), _lib._ptr(volt), _lib._ptr(curr),
                                            1 if accumulate else 0, _lib._ptr(iters), _lib._ptr(relres))
+        self._raise(rc, raise_on_residual)
+        if self.io_dtype != self.dtype:
+            R = R.astype(self.io_dtype)
+            volt = None if volt is None else volt.astype(self.io_dtype)
+            curr = None if curr is None else curr.astype(self.io_dtype)
+        return dict(R=R, volt=volt, curr=curr, iters=iters, relres=relres)
+
+    def solve_pairs_superposed(self, nodes, pi, pj, weight=None, want_volt=False, want_curr=False,
+                               accumulate=False, rtol=None, itmax=None, raise_on_residual=True):
+        """All pairs (nodes[pi[c]], nodes[pj[c]]) of one component from len(nodes)-1 solves
+        (cs_b200_solve_pairs_superposed).  Same outputs as solve_pairs; `iters` are the
+        iterations of the point solves."""
+        nodes = np.ascontiguousarray(nodes, dtype=np.int64)
+        pi = np.ascontiguousarray(pi, dtype=np.int64)
+        pj = np.ascontiguousarray(pj, dtype=np.int64)
+        k = len(pi)
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        R = np.zeros(k, dtype=self.dtype)
+        volt = np.empty((self.n, k), dtype=self.dtype, order="F") if want_volt else None
+        curr = np.empty((self.n, k), dtype=self.dtype, order="F") if want_curr else None
+        iters = np.zeros(max(len(nodes) - 1, 1), dtype=np.int64)
+        relres = np.zeros(k, dtype=np.float64)
+        rc = self._lib.cs_b200_solve_pairs_superposed(
+            self._h, len(nodes), _lib._ptr(nodes), k, _lib._ptr(pi), _lib._ptr(pj), _lib._ptr(w),
+            self.solver.rtol if rtol is None else rtol, self.solver.itmax if itmax is None else itmax,
+            _lib._ptr(R), _lib._ptr(volt), _lib._ptr(curr), 1 if accumulate else 0, _lib._ptr(iters),
+            _lib._ptr(relres))
         self._raise(rc, raise_on_residual)
         if self.io_dtype != self.dtype:
             R = R.astype(self.io_dtype)

@@ -170,6 +170,20 @@ int cs_b200_solve_pairs(cs_b200_handle* h, int64_t k, const int64_t* src, const 
                         void* volt, void* curr, int accumulate, int64_t* iters,
                         double* relres);
 
+/* Pairwise driver by SUPERPOSITION -- the reference's Shortcut (src/core.jl:685-739), extended
+ * to voltage / current maps.  All pairs among `np` focal nodes of ONE connected component share
+ * the operator and are linear in the right-hand side, so np-1 solves
+ *     A u_x = e_{nodes[x]} - e_{nodes[0]} ,  u_x -= u_x[nodes[0]]        (x = 1 .. np-1, u_0 = 0)
+ * give every pair:  v(i,j) = u_j - u_i , shifted so that v[src] = 0 , R = v[dst].
+ * pi / pj: the k pairs as indices into `nodes` (src = nodes[pi[c]], dst = nodes[pj[c]]).
+ * R, volt, curr, accumulate, weight: exactly as cs_b200_solve_pairs.  Each combined voltage is
+ * put through the true-residual gate against its own right-hand side (relres[k]); point_iters
+ * (np-1 values, may be NULL) are the iterations of the point solves.  Needs np-1 device vectors.  */
+int cs_b200_solve_pairs_superposed(cs_b200_handle* h, int64_t np, const int64_t* nodes, int64_t k,
+                                   const int64_t* pi, const int64_t* pj, const double* weight,
+                                   double rtol, int64_t itmax, void* R, void* volt, void* curr,
+                                   int accumulate, int64_t* point_iters, double* relres);
+
 /* Batched solve with SPARSE right-hand sides, device-resident -- the advanced-mode kernel
  * (src/raster/advanced.jl:274-305) for source/ground sets without finite grounds, and
  * the all-to-one loop built on it (src/raster/onetoall.jl:110-118,146-151):

@@ -55,6 +55,10 @@ class FakeFactor:
         return dict(R=R, volt=V if want_volt else None, curr=curr if want_curr else None,
                     iters=np.zeros(k, dtype=np.int64), relres=np.zeros(k))
 
+    def solve_pairs_superposed(self, nodes, pi, pj, weight=None, **kw):
+        nodes = np.asarray(nodes)
+        return self.solve_pairs(nodes[np.asarray(pi)], nodes[np.asarray(pj)], weight, **kw)
+
     def solve_rhs(self, rhs, **kw):
         import scipy.sparse.linalg as spla
         rhs = np.asarray(rhs, dtype=np.float64)

@@ -361,6 +361,37 @@ def test_compute_omniscape_current_on_device():
     assert np.abs(cur - ref).max() < 1e-7 * ref.max()
 
 
+@pytest.mark.parametrize("precond", ["jacobi", "amg"])
+def test_superposed_pairs_equal_direct_pairs(precond):
+    """v(i,j) = u_j - u_i from np-1 point solves == one solve per pair (resistances, voltages,
+    per-pair node currents, cumulative / max maps), each pair through its own residual gate."""
+    A = holey_raster(70, 60, seed=31)
+    nodes = graph.focal_nodes(A.shape[0], 6, seed=3)
+    src, dst = graph.all_pairs(nodes)
+    w = np.arange(1, len(src) + 1, dtype=np.float64)
+    nn, inv = np.unique(np.concatenate([src, dst]), return_inverse=True)
+    pi, pj = inv[:len(src)], inv[len(src):]
+    with cb.B200Factor(A, cb.CUDASolver(precond=precond, rtol=1e-11)) as f:
+        a = f.solve_pairs(src, dst, w, want_volt=True, want_curr=True, accumulate=True)
+        ca, ma = f.read_currents()
+        f.reset_currents()
+        b = f.solve_pairs_superposed(nn, pi, pj, w, want_volt=True, want_curr=True, accumulate=True)
+        cb_, mb = f.read_currents()
+    assert len(b["iters"]) == len(nn) - 1 and b["iters"].max() > 0
+    assert b["relres"].max() < 1e-6
+    assert np.abs(b["R"] - a["R"]).max() <= 1e-8 * np.abs(a["R"]).max()
+    assert np.abs(b["volt"] - a["volt"]).max() <= 1e-7 * np.abs(a["volt"]).max()
+    assert np.abs(b["curr"] - a["curr"]).max() <= 1e-6 * np.abs(a["curr"]).max()
+    assert np.abs(cb_ - ca).max() <= 1e-6 * np.abs(ca).max()
+    assert np.abs(mb - ma).max() <= 1e-6 * np.abs(ma).max()
+
+
+@pytest.mark.parametrize("i", [1, 3, 12])
+def test_golden_raster_pairwise_superposed(golden, i):
+    r, exp = cases.run_raster_pairwise(golden, f"sgVerify{i}", cb.CUDASolver(superpose=True, rtol=1e-8))
+    cases.check_raster_pairwise(r, exp)
+
+
 def test_bad_pairs_rejected():
     A = holey_raster(10, 10, seed=1)
     with cb.B200Factor(A, cb.CUDASolver()) as f:

@@ -155,3 +155,16 @@ def test_compute_omniscape_current_window_with_holes():
         k[g <= 0] = 0
     cur = cb.compute_omniscape_current(g, src, gnd, {"connect_four_neighbors_only": "True", "solver": "cuda"})
     assert cur.shape == g.shape and np.all(cur[g <= 0] == 0) and cur.max() > 0
+
+
+@pytest.mark.parametrize("i", [1, 2, 5, 9, 16])
+def test_raster_pairwise_driver_superposed(golden, i):
+    """CUDASolver(superpose=True): the driver hands each component's pairs to
+    solve_pairs_superposed as (nodes, pi, pj); outputs must still meet the goldens."""
+    r, exp = cases.run_raster_pairwise(golden, f"sgVerify{i}", cb.CUDASolver(superpose=True))
+    cases.check_raster_pairwise(r, exp, rel=1e-7)
+
+
+def test_network_pairwise_driver_superposed(golden):
+    prob, flags, exp = cases.network_pairwise_problem(golden, "sgNetworkVerify2", cb.CUDASolver(superpose=True))
+    cases.check_network_pairwise(cb.single_ground_all_pairs(prob, flags), exp)
