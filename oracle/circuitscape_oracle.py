@@ -11,7 +11,7 @@ Every function cites the reference file:line (relative to /root/reference) it
 follows.  Parity status: PINNED -- `tests/test_oracle_golden.py` checks it
 against every golden vector the reference's own integration suite holds for
 this path (test/output_verify sgVerify1-17, sgNetworkVerify1-3, mgVerify1-6,
-mgNetworkVerify1-3; packed by tests/golden/make_fixtures.py) with the
+mgNetworkVerify1-3, oneToAllVerify1-13, allToOneVerify1-12; packed by tests/golden/make_fixtures.py) with the
 reference's own tolerances (test/test_utils.jl:72-73,147,196,217-226).
 
 Linear solves: the reference's arithmetic lives in un-vendored Julia packages
