@@ -17,6 +17,7 @@ from .fake_factor import FakeFactor
 @pytest.fixture(autouse=True)
 def fake_device(monkeypatch):
     monkeypatch.setattr(S, "construct_cholesky_factor", lambda m, s, **kw: FakeFactor(m, s, **kw))
+    monkeypatch.setattr(S, "multiple_solve", lambda s, m, b: FakeFactor(m, s).solve_rhs(np.asarray(b))[0])
 
 
 @st.composite
@@ -71,3 +72,44 @@ def test_pairwise_driver_matches_oracle(p, superpose):
         assert np.abs(got.cum_curmap - want.cum_curmap).max() < 1e-8
     if want.max_curmap is not None:
         assert np.abs(got.max_curmap - want.max_curmap).max() < 1e-8
+
+
+@st.composite
+def advanced_problems(draw):
+    nr, nc = draw(st.integers(3, 7)), draw(st.integers(3, 7))
+    rng = np.random.default_rng(draw(st.integers(0, 2**31 - 1)))
+    g = rng.uniform(0.2, 4.0, (nr, nc))
+    g[rng.random((nr, nc)) < draw(st.sampled_from([0.0, 0.2]))] = 0.0
+    src = np.where(rng.random((nr, nc)) < 0.15, rng.uniform(0.5, 2.0, (nr, nc)), 0.0)
+    kind = draw(st.sampled_from(["finite", "inf", "mixed"]))
+    gm = np.where(rng.random((nr, nc)) < 0.15, rng.uniform(0.5, 2.0, (nr, nc)), 0.0)
+    if kind == "inf":
+        gm = np.where(gm != 0, np.inf, 0.0)
+    elif kind == "mixed":
+        gm = np.where((gm != 0) & (rng.random((nr, nc)) < 0.5), np.inf, gm)
+    policy = draw(st.sampled_from(["keepall", "rmvsrc", "rmvgnd", "rmvall"]))
+    return g, src, gm, policy, draw(st.booleans())
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(p=advanced_problems())
+def test_advanced_driver_matches_oracle(p):
+    g, src, gm, policy, four = p
+    nodemap = graph.construct_node_map(g, None)
+    if nodemap.max() == 0:
+        return
+    G = graph.laplacian(graph.construct_graph(g, nodemap, False, four))
+    cc = graph.connected_components(G)
+    n = G.shape[0]
+    s_o, g_o, f_o = co._sources_grounds_raster(src, gm, nodemap, n, policy)
+    s_p, g_p, f_p = cb.core.sources_and_grounds_from_maps(src, gm, nodemap, n, policy)
+    assert np.array_equal(s_o, s_p) and np.array_equal(g_o, g_p) and np.array_equal(f_o, f_p)
+    try:
+        want = co.advanced_kernel(G, cc, s_o, g_o, f_o, nodemap, None, g)
+    except Exception:
+        return                                   # singular set-ups (source component without a path to ground)
+    got = cb.advanced_kernel(cb.AdvancedProblem(G, cc, s_p, g_p, f_p, nodemap, None, g, cb.CUDASolver()),
+                             cb.Flags(is_raster=True, is_advanced=True))
+    assert np.abs(got.voltages - want.voltages).max() < 1e-8 * max(1.0, np.abs(want.voltages).max())
+    assert np.abs(got.voltmap - want.voltmap).max() < 1e-8 * max(1.0, np.abs(want.voltmap).max())
+    assert np.abs(got.curmap - want.curmap).max() < 1e-8 * max(1.0, np.abs(want.curmap).max())
