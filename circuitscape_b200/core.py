@@ -207,6 +207,9 @@ def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=
         for a, b in zero:
             R[a, b] = R[b, a] = 0.0
         if not solves:
+            if shortcut:      # duplicates on the anchor only: the reference still runs the update (core.jl:504-506)
+                anchor = int(np.nonzero(points == csub[0])[0][0])
+                _update_shortcut_resistances(anchor, voltmatrix, shortcut_res, R, points, comp)
             continue
         rows = comp - 1
         matrix = G[rows][:, rows].tocsr()
