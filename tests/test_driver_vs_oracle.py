@@ -113,3 +113,115 @@ def test_advanced_driver_matches_oracle(p):
     assert np.abs(got.voltages - want.voltages).max() < 1e-8 * max(1.0, np.abs(want.voltages).max())
     assert np.abs(got.voltmap - want.voltmap).max() < 1e-8 * max(1.0, np.abs(want.voltmap).max())
     assert np.abs(got.curmap - want.curmap).max() < 1e-8 * max(1.0, np.abs(want.curmap).max())
+
+
+@st.composite
+def onetoall_problems(draw):
+    nr, nc = draw(st.integers(3, 7)), draw(st.integers(3, 7))
+    rng = np.random.default_rng(draw(st.integers(0, 2**31 - 1)))
+    g = rng.uniform(0.2, 4.0, (nr, nc))
+    g[rng.random((nr, nc)) < draw(st.sampled_from([0.0, 0.15]))] = -9999.0
+    npts = draw(st.integers(2, 5))
+    cells = rng.choice(nr * nc, size=npts, replace=False)
+    pm = np.zeros((nr, nc))
+    ids = np.arange(1, npts + 1)
+    if draw(st.booleans()) and npts >= 3:
+        ids[-1] = ids[0]                                  # two cells carry one focal id (a focal region)
+    pm.ravel()[cells] = ids
+    poly = None
+    if draw(st.booleans()):
+        poly = np.zeros((nr, nc))
+        poly[rng.random((nr, nc)) < 0.2] = 1
+        poly[rng.random((nr, nc)) < 0.1] = 2
+    strengths = None
+    if draw(st.booleans()):
+        u = np.unique(ids)
+        strengths = np.column_stack([u, rng.uniform(0.5, 3.0, len(u))])
+    scenario = draw(st.sampled_from(["one-to-all", "all-to-one"]))
+    maps = draw(st.sampled_from(["cur", "volt+cur+max", "cum_only"]))
+    return g, pm, poly, strengths, scenario, maps, draw(st.booleans())
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(p=onetoall_problems())
+def test_onetoall_driver_matches_oracle(p):
+    g, pm, poly, strengths, scenario, maps, four = p
+    nr, nc = g.shape
+    meta = np.array([nc, nr, 0.0, 0.0, 1.0])
+    cfg = {"scenario": scenario, "data_type": "raster", "habitat_map_is_resistances": "False",
+           "write_cur_maps": str(maps in ("cur", "volt+cur+max")), "write_volt_maps": str(maps == "volt+cur+max"),
+           "write_max_cur_maps": str(maps == "volt+cur+max"), "write_cum_cur_map_only": str(maps == "cum_only"),
+           "use_polygons": str(poly is not None), "use_variable_source_strengths": str(strengths is not None),
+           "connect_four_neighbors_only": str(four)}
+    inputs = {"habitat_file": ("grid", g, meta), "point_file": ("grid", pm, meta)}
+    if poly is not None:
+        inputs["polygon_file"] = ("grid", poly, meta)
+    if strengths is not None:
+        inputs["variable_source_file"] = ("txtlist", strengths, np.zeros(0))
+    try:
+        want = co.raster_one_to_all(cfg, inputs)
+    except (ValueError, IndexError):
+        return        # inputs the reference rejects too: < 2 valid focal nodes, strengths with focal regions
+    cellmap, polymap, _, inc = co.load_raster_inputs(cfg, inputs)
+    points_rc = co.read_point_map("grid", pm, meta)
+    data = cb.RasterData(cellmap, polymap, points_rc, None if strengths is None else strengths.copy(), inc)
+    flags = cb.Flags.from_cfg(cfg)
+    got = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(), four_neighbors=four, avg_res=False)
+    assert got.resistances.shape == want.resistances.shape
+    assert np.abs(got.resistances - want.resistances).max() < 1e-8 * max(1.0, np.abs(want.resistances).max())
+    assert set(got.curmaps) == set(want.curmaps) and set(got.voltmaps) == set(want.voltmaps)
+    for k in want.curmaps:
+        assert np.abs(got.curmaps[k] - want.curmaps[k]).max() < 1e-8 * max(1.0, np.abs(want.curmaps[k]).max())
+    for k in want.voltmaps:
+        assert np.abs(got.voltmaps[k] - want.voltmaps[k]).max() < 1e-8 * max(1.0, np.abs(want.voltmaps[k]).max())
+    assert np.abs(got.cum_curmap - want.cum_curmap).max() < 1e-8 * max(1.0, np.abs(want.cum_curmap).max())
+    if want.max_curmap is not None:
+        assert np.abs(got.max_curmap - want.max_curmap).max() < 1e-8 * max(1.0, np.abs(want.max_curmap).max())
+
+
+@st.composite
+def networks(draw):
+    n = draw(st.integers(4, 12))
+    rng = np.random.default_rng(draw(st.integers(0, 2**31 - 1)))
+    edges = {(i, i + 1) for i in range(1, n) if rng.random() < 0.85}       # mostly a path: a few components
+    for _ in range(draw(st.integers(0, 2 * n))):
+        a, b = rng.integers(1, n + 1, 2)
+        if a != b:
+            edges.add((min(a, b), max(a, b)))
+    if not edges:
+        edges = {(1, 2)}
+    e = np.array(sorted(edges), dtype=np.float64)
+    if 1 not in e[:, :2]:
+        e = np.vstack([e, [1, 2]])
+    raw = np.column_stack([e, rng.uniform(0.2, 3.0, len(e))])
+    nn = int(raw[:, :2].max())
+    k = draw(st.integers(2, min(5, nn)))
+    fp = np.sort(rng.choice(np.arange(1, nn + 1), size=k, replace=False))
+    return raw, fp
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(p=networks(), superpose=st.booleans())
+def test_network_pairwise_driver_matches_oracle(p, superpose):
+    raw, fp = p
+    cfg = {"data_type": "network", "scenario": "pairwise", "habitat_map_is_resistances": "False",
+           "write_cur_maps": "True", "write_volt_maps": "True"}
+    inputs = {"habitat_file": ("txtlist", raw, np.zeros(0)), "point_file": ("txtlist", fp.reshape(-1, 1), np.zeros(0))}
+    want = co.network_pairwise(cfg, inputs)
+    i, j, v, _ = co.load_graph(raw, False)
+    G, cc = co.network_graph(i, j, v)
+    flags = cb.Flags.from_cfg(cfg)
+    got = cb.single_ground_all_pairs(cb.GraphProblem(G, cc, fp, fp, set(), None, None, None,
+                                                     cb.CUDASolver(superpose=superpose), (i, j)), flags)
+    assert np.abs(got.resistances - want.resistances).max() < 1e-8 * max(1.0, np.abs(want.resistances).max())
+    assert set(got.curmaps) == set(want.curmaps)
+    for k in want.curmaps:
+        gn, gc_ = got.curmaps[k]
+        wn, wc = want.curmaps[k]
+        assert np.array_equal(np.asarray(gn), np.asarray(wn))
+        assert np.abs(gc_ - wc).max() < 1e-8 * max(1.0, np.abs(wc).max())
+        srt = lambda t: (lambda m: m[np.lexsort(m.T[::-1])])(np.column_stack([np.asarray(x, dtype=float) for x in t]))
+        gb, wb = srt(got.branch[k]), srt(want.branch[k])      # row order is not pinned (test_utils.jl sorts too)
+        assert gb.shape == wb.shape and np.abs(gb - wb).max(initial=0.0) < 1e-8
+    assert np.abs(got.cum_node - want.cum_node).max() < 1e-8 * max(1.0, np.abs(want.cum_node).max())
+    assert np.abs(got.cum_branch - want.cum_branch).max() < 1e-8 * max(1.0, np.abs(want.cum_branch).max())
