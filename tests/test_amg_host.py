@@ -186,3 +186,99 @@ def test_windowed_form_matches_csr(harness):
         if expect_win:
             assert nwin >= 0.95 * nb.value, (name, nwin, nb.value)
             assert mw.value <= 512
+
+
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+import scipy.sparse.linalg as spla  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(nr=st.integers(15, 40), nc=st.integers(15, 40), seed=st.integers(0, 2**31 - 1),
+       sigma=st.sampled_from([0.0, 1.0, 2.5]), holes=st.sampled_from([0.0, 0.1, 0.3]), four=st.booleans(),
+       grounded=st.booleans())
+def test_random_rasters_give_a_sound_hierarchy(harness, nr, nc, seed, sigma, holes, four, grounded):
+    """Whatever raster comes in (contrast, holes, 4/8 neighbours, singular or grounded): R = P^T,
+    Galerkin coarse operators, a symmetric V-cycle, and PCG converging to the true solution."""
+    rng = np.random.default_rng(seed)
+    g = np.exp(rng.normal(0.0, sigma, (nr, nc))) if sigma > 0 else rng.uniform(0.1, 1.0, (nr, nc))
+    g[rng.random((nr, nc)) < holes] = 0.0
+    nm = graph.construct_node_map(g)
+    if nm.max() < 2:
+        return
+    G = graph.laplacian(graph.construct_graph(g, nm, False, four))
+    comp = max(graph.connected_components(G), key=len) - 1
+    if len(comp) < 2:
+        return
+    A = G[comp][:, comp].tocsr()
+    n = A.shape[0]
+    if grounded:
+        d = np.zeros(n); d[rng.integers(0, n)] = rng.uniform(0.1, 2.0)
+        A = (A + sp.diags(d)).tocsr()
+    levels, pinv = build(harness, A)
+    for l in range(len(levels) - 1):
+        L = levels[l]
+        assert abs(L["R"] - L["P"].T).max() < 1e-15
+        Ac = (L["R"] @ L["A"] @ L["P"]).tocsr()
+        assert abs(Ac - levels[l + 1]["A"]).max() <= 1e-12 * max(1e-300, abs(Ac).max())
+        # damped Jacobi must stay convergent on every level: omega * lambda_max(D^-1 A) < 2
+        d = L["A"].diagonal()
+        if d.min() > 0 and L["A"].shape[0] > 2:
+            Dm = sp.diags(1.0 / np.sqrt(d))
+            lam = spla.eigsh((Dm @ L["A"] @ Dm).asfptype(), k=1, which="LA", return_eigenvectors=False, tol=1e-4)[0]
+            assert 0 < L["omega"] * lam < 2.0, (L["omega"], lam)
+    M = (lambda r: vcycle(levels, pinv, r)) if len(levels) > 1 else None
+    if M is not None:
+        u, w = rng.standard_normal(n), rng.standard_normal(n)
+        if not grounded:
+            u -= u.mean(); w -= w.mean()
+        assert abs(u @ M(w) - w @ M(u)) <= 1e-9 * (np.linalg.norm(u) * np.linalg.norm(M(w)) + 1e-300)
+        assert u @ M(u) > 0
+    b = np.zeros(n); b[0] += 1.0; b[n - 1] -= 1.0
+    if grounded:
+        b[0] += 0.5
+    x, it = pcg(A, b, M if M is not None else (lambda r: r / A.diagonal()), rtol=1e-8, itmax=400)
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 1e-5
+    if M is not None:
+        assert it <= 120, it
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(1, 700), ncols=st.integers(1, 900), seed=st.integers(0, 2**31 - 1),
+       kind=st.sampled_from(["banded", "two-bands", "scattered", "long-rows", "empty-rows"]))
+def test_windowed_form_random_rectangular(harness, n, ncols, seed, kind):
+    """win_host.hpp on arbitrary rectangular CSR (the transfer operators are rectangular): segment
+    windows, the direct-gather fallback for blocks that do not fit, rows longer than a block,
+    empty rows -- the host emulation of the kernel's walk must reproduce y = A x."""
+    harness.winh_spmv_rect.restype = C.c_long
+    harness.winh_spmv_rect.argtypes = [C.c_long, C.c_long, C.c_long] + [C.c_void_p] * 7
+    rng = np.random.default_rng(seed)
+    rows, cols = [], []
+    for i in range(n):
+        c0 = int(i * ncols / max(n, 1))
+        if kind == "banded":
+            cs = c0 + rng.integers(-4, 5, size=rng.integers(1, 8))
+        elif kind == "two-bands":
+            cs = np.concatenate([c0 + rng.integers(-2, 3, 3), (c0 + ncols // 2) % ncols + rng.integers(-2, 3, 3)])
+        elif kind == "scattered":
+            cs = rng.integers(0, ncols, size=rng.integers(1, 12))
+        elif kind == "long-rows":
+            cs = rng.integers(0, ncols, size=1300 if i % 97 == 0 else 3)
+        else:
+            cs = c0 + rng.integers(-3, 4, size=0 if i % 3 == 0 else 4)
+        cs = np.unique(np.clip(cs, 0, ncols - 1))
+        rows += [i] * len(cs); cols += list(cs)
+    A = sp.csr_matrix((rng.standard_normal(len(rows)), (rows, cols)), shape=(n, ncols))
+    A.sort_indices()
+    if A.nnz == 0:
+        return
+    x = rng.standard_normal(ncols)
+    y = np.full(n, np.nan)
+    ptr = A.indptr.astype(np.int32); idx = A.indices.astype(np.int32); val = A.data.astype(np.float64)
+    nb, mw = C.c_long(), C.c_long()
+    nwin = harness.winh_spmv_rect(n, ncols, A.nnz, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data,
+                                  x.ctypes.data, y.ctypes.data, C.byref(nb), C.byref(mw))
+    assert nwin >= 0
+    ref = A @ x
+    assert np.all(np.isfinite(y))
+    assert np.abs(y - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    assert mw.value <= 1024
