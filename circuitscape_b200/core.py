@@ -567,6 +567,66 @@ class OneToAllOutput:
     num_solves: int = 0
 
 
+def _all_to_one_batched_raster(G, comps, nodemap, newpoly, point_map, unique_point_map, uniq, rr, cc_,
+                                strengths, solver, o):
+    """All-to-one without include/exclude lists: every iteration keeps the same node map and operator
+    and differs only in which focal node is tied to ground, so the iterations of one connected
+    component are columns of ONE sparse-RHS batch on the component's singular Laplacian
+    (cs_b200_solve_sources; ground = reference row carrying minus the summed sources) instead of
+    one factor + solve per iteration (src/raster/onetoall.jl:110-151 through
+    src/raster/advanced.jl:274-305).  Returns {iteration index: (voltage raster, current raster)}
+    for the iterations it could serve; the caller runs the rest through the per-iteration path."""
+    n_nodes = G.shape[0]
+    strength_map = None
+    if strengths is not None:
+        strength_map = np.zeros(point_map.shape)
+        strength_map[rr - 1, cc_ - 1] = strengths[:, 1] if len(strengths) == len(rr) else 0.0
+        if len(strengths) != len(rr):
+            return {}
+    plans = {}      # component index -> list of (iteration, ground node, source nodes, source values)
+    comp_of = np.zeros(n_nodes + 1, dtype=np.int64) - 1
+    for ci, comp in enumerate(comps):
+        comp_of[np.asarray(comp)] = ci
+    for i, n in enumerate(uniq):
+        if point_map.sum() == n:
+            continue
+        if strength_map is not None:
+            source_map = np.where(unique_point_map == n, 0.0, strength_map)
+        else:
+            source_map = np.where((unique_point_map != 0) & (point_map != n), 1.0, 0.0)
+        ground_map = np.where(point_map == n, np.inf, 0.0)
+        s_, g_, f_ = sources_and_grounds_from_maps(source_map, ground_map, nodemap, n_nodes, "rmvsrc")
+        gnodes = np.nonzero(np.isinf(g_))[0]
+        check_node = nodemap[rr[i] - 1, cc_[i] - 1]
+        if len(gnodes) != 1 or f_[0] != NODATA or check_node == 0:
+            continue                                   # several ground nodes: per-iteration path
+        ci = comp_of[check_node]
+        if ci < 0 or comp_of[gnodes[0] + 1] != ci:
+            continue
+        rows = np.asarray(comps[ci]) - 1
+        local = np.zeros(n_nodes, dtype=np.int64) - 1
+        local[rows] = np.arange(len(rows))
+        src_nodes = np.nonzero(s_[rows] != 0)[0]
+        if len(src_nodes) == 0:
+            continue
+        plans.setdefault(ci, []).append((i, int(local[gnodes[0]]), src_nodes, s_[rows][src_nodes]))
+    served = {}
+    for ci, items in plans.items():
+        rows = np.asarray(comps[ci]) - 1
+        a_local = G[rows][:, rows].tocsr()
+        lm = construct_local_node_map(nodemap, np.asarray(comps[ci]), newpoly)
+        columns, refs = [], []
+        for _, gl, sn, sv in items:
+            columns.append((np.concatenate([sn, [gl]]), np.concatenate([sv, [-sv.sum()]])))
+            refs.append(gl)
+        with S.construct_cholesky_factor(a_local, solver) as factor:
+            r = factor.solve_sources(columns, refs, want_volt=True, want_curr=True)
+        for c, (i, *_rest) in enumerate(items):
+            served[i] = (_scatter(r["volt"][:, c].astype(np.float64), lm),
+                         _scatter(r["curr"][:, c].astype(np.float64), lm))
+    return served
+
+
 def onetoall_kernel(data: RasterData, flags: Flags, cfg, solver=None, one_to_all=None,
                     four_neighbors=False, avg_res=False) -> OneToAllOutput:
     """src/raster/onetoall.jl:13-167.  One advanced-mode solve per focal id: one-to-all = unit
@@ -605,6 +665,10 @@ def onetoall_kernel(data: RasterData, flags: Flags, cfg, solver=None, one_to_all
     out.max_curmap = np.full(gmap.shape, NODATA) if o.write_max_cur_maps else None
     res = np.zeros(len(uniq))
     strength_map = np.zeros(gmap.shape) if strengths is not None else None
+    batched = {}
+    if (not one_to_all) and inc is None and getattr(solver, "batch_all_to_one", False):
+        batched = _all_to_one_batched_raster(G, comps, nodemap, newpoly, point_map, unique_point_map, uniq,
+                                             rr, cc_, strengths, solver, o)
     for i, n in enumerate(uniq):
         pm, nm, npoly = point_map.copy(), nodemap, newpoly
         if inc is not None:
@@ -619,6 +683,18 @@ def onetoall_kernel(data: RasterData, flags: Flags, cfg, solver=None, one_to_all
             strength_map[rr - 1, cc_ - 1] = st[:, 1]
         if pm.sum() == n:                                           # no other focal node left
             res[i] = -1
+            continue
+        if i in batched:                                            # solved as a column of the batch
+            outvolt, outcurr = batched[i]
+            out.num_solves += 1
+            res[i] = 0
+            if o.write_volt_maps:
+                out.voltmaps[n] = outvolt
+            if o.write_cur_maps or o.write_cum_cur_map_only:
+                out.curmaps[n] = outcurr
+            out.cum_curmap += outcurr
+            if out.max_curmap is not None:
+                out.max_curmap = np.maximum(out.max_curmap, outcurr)
             continue
         if one_to_all:
             strv = strengths[i, 1] if strengths is not None else 1.0

@@ -43,6 +43,7 @@ class CUDASolver:
     f32_compute: bool = False        # precision = single: keep fp32 ON THE DEVICE too (see B200Factor)
     mixed: bool = True               # fp64 + AMG: fp32 V-cycle inside fp64 CG
     superpose: bool = False          # pairwise driver: one solve per focal NODE, pairs by superposition
+    batch_all_to_one: bool = False   # all-to-one: every iteration a column of ONE batch on one operator
 
     @property
     def dtype(self):

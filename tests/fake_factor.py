@@ -59,6 +59,28 @@ class FakeFactor:
         nodes = np.asarray(nodes)
         return self.solve_pairs(nodes[np.asarray(pi)], nodes[np.asarray(pj)], weight, **kw)
 
+    def solve_sources(self, columns, ref, probe=None, weight=None, want_volt=False, want_curr=False,
+                      accumulate=False, **kw):
+        import scipy.sparse.linalg as spla
+        k = len(columns)
+        V = np.zeros((self.n, k))
+        for c, (rows, vals) in enumerate(columns):
+            b = np.zeros(self.n)
+            np.add.at(b, np.asarray(rows, dtype=np.int64), np.asarray(vals, dtype=np.float64))
+            keep = np.setdiff1d(np.arange(self.n), [ref[c]])
+            V[keep, c] = spla.splu(self.A[keep][:, keep].tocsc()).solve(b[keep])
+        curr = np.zeros((self.n, k))
+        w = np.ones(k) if weight is None else np.asarray(weight, dtype=float)
+        if want_curr or accumulate:
+            for c in range(k):
+                curr[:, c] = co.get_node_currents(self.A, V[:, c])
+                if accumulate:
+                    self.cum += w[c] * curr[:, c]
+                    self.mx = np.maximum(self.mx, curr[:, c])
+        pv = None if probe is None else V[np.asarray(probe)].T.copy()
+        return dict(probe_volt=pv, volt=V if want_volt else None, curr=curr if want_curr else None,
+                    iters=np.zeros(k, dtype=np.int64), relres=np.zeros(k))
+
     def solve_rhs(self, rhs, **kw):
         import scipy.sparse.linalg as spla
         rhs = np.asarray(rhs, dtype=np.float64)

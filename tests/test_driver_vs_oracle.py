@@ -143,8 +143,8 @@ def onetoall_problems(draw):
 
 
 @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
-@given(p=onetoall_problems())
-def test_onetoall_driver_matches_oracle(p):
+@given(p=onetoall_problems(), batched=st.booleans())
+def test_onetoall_driver_matches_oracle(p, batched):
     g, pm, poly, strengths, scenario, maps, four = p
     nr, nc = g.shape
     meta = np.array([nc, nr, 0.0, 0.0, 1.0])
@@ -166,7 +166,8 @@ def test_onetoall_driver_matches_oracle(p):
     points_rc = co.read_point_map("grid", pm, meta)
     data = cb.RasterData(cellmap, polymap, points_rc, None if strengths is None else strengths.copy(), inc)
     flags = cb.Flags.from_cfg(cfg)
-    got = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(), four_neighbors=four, avg_res=False)
+    got = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(batch_all_to_one=batched),
+                             four_neighbors=four, avg_res=False)
     assert got.resistances.shape == want.resistances.shape
     assert np.abs(got.resistances - want.resistances).max() < 1e-8 * max(1.0, np.abs(want.resistances).max())
     assert set(got.curmaps) == set(want.curmaps) and set(got.voltmaps) == set(want.voltmaps)
