@@ -567,6 +567,76 @@ class OneToAllOutput:
     num_solves: int = 0
 
 
+def _one_to_all_batched_raster(G, comps, nodemap, newpoly, point_map, unique_point_map, uniq, rr, cc_,
+                               strengths, solver):
+    """One-to-all without include/exclude lists: iteration p puts a current source on focal node p and
+    ties every OTHER focal node to ground (src/raster/onetoall.jl:100-109).  With F the focal nodes of
+    a component and N the rest, all iterations share B = L[N, N] (the Laplacian with every focal
+    row/column deleted, SPD); block elimination of the one live focal node gives
+        B w_p = -L[N, p] ,   v_p = s_p / (L[p, p] + L[p, N] w_p) ,   v_N = v_p w_p ,   v = 0 on the other focal nodes,
+    so the iterations of a component are columns of ONE n_N x |F| batch on one factor (hook #2) instead
+    of one factor + solve per iteration.  Returns {iteration: (voltage raster, current raster,
+    source-cell voltage / strength)}; iterations it cannot serve take the per-iteration path."""
+    n_nodes = G.shape[0]
+    if strengths is not None and len(strengths) != len(uniq):
+        return {}
+    comp_of = np.zeros(n_nodes + 1, dtype=np.int64) - 1
+    for ci, comp in enumerate(comps):
+        comp_of[np.asarray(comp)] = ci
+    plans = {}
+    for i, n in enumerate(uniq):
+        if point_map.sum() == n:
+            continue
+        strv = float(strengths[i, 1]) if strengths is not None else 1.0
+        source_map = np.where(unique_point_map == n, strv, 0.0)
+        ground_map = np.where((point_map != n) & (point_map > 0), np.inf, 0.0)
+        s_, g_, f_ = sources_and_grounds_from_maps(source_map, ground_map, nodemap, n_nodes, "rmvgnd")
+        check_node = nodemap[rr[i] - 1, cc_[i] - 1]
+        snodes = np.nonzero(s_ != 0)[0]
+        if len(snodes) != 1 or f_[0] != NODATA or check_node == 0 or not np.all(np.isinf(g_[g_ != 0])):
+            continue
+        ci = comp_of[check_node]
+        if ci < 0 or comp_of[snodes[0] + 1] != ci:
+            continue
+        rows = np.asarray(comps[ci]) - 1
+        if not np.any(np.isinf(g_[rows])):
+            continue                                   # no ground in this component: nothing is solved
+        plans.setdefault(ci, []).append((i, int(snodes[0]), float(s_[snodes[0]]),
+                                         frozenset(np.nonzero(np.isinf(g_[rows]))[0].tolist())))
+    served = {}
+    for ci, items in plans.items():
+        rows = np.asarray(comps[ci]) - 1
+        local = np.zeros(n_nodes, dtype=np.int64) - 1
+        local[rows] = np.arange(len(rows))
+        a_local = G[rows][:, rows].tocsr()
+        F = sorted({int(local[p]) for _, p, _, _ in items} | set().union(*[g for *_x, g in items]))
+        # every served iteration must ground exactly F minus its own source node
+        items = [it for it in items if it[3] == frozenset(F) - {int(local[it[1]])}]
+        if not items or len(F) >= len(rows):
+            continue
+        Nidx = np.setdiff1d(np.arange(len(rows)), F)
+        B = a_local[Nidx][:, Nidx].tocsr()
+        cols = [int(local[p]) for _, p, _, _ in items]
+        rhs = -a_local[Nidx][:, cols].toarray()
+        if not np.any(rhs):
+            continue
+        live = np.nonzero(np.abs(rhs).sum(axis=0) > 0)[0]
+        W = np.zeros_like(rhs)
+        with S.construct_cholesky_factor(B, solver) as factor:
+            W[:, live] = np.asarray(S.solve_linear_system(factor, B, np.asfortranarray(rhs[:, live]))).reshape(len(Nidx), -1)
+        lm = construct_local_node_map(nodemap, np.asarray(comps[ci]), newpoly)
+        for c, (i, p, sval, _) in enumerate(items):
+            pl = cols[c]
+            lpn = a_local[pl, Nidx].toarray().ravel()
+            denom = a_local[pl, pl] + lpn @ W[:, c]
+            v = np.zeros(len(rows))
+            v[pl] = sval / denom
+            v[Nidx] = v[pl] * W[:, c]
+            cur = node_currents_host(a_local, v, None)
+            served[i] = (_scatter(v, lm), _scatter(cur, lm), v[pl] / sval)
+    return served
+
+
 def _all_to_one_batched_raster(G, comps, nodemap, newpoly, point_map, unique_point_map, uniq, rr, cc_,
                                 strengths, solver, o):
     """All-to-one without include/exclude lists: every iteration keeps the same node map and operator
@@ -669,6 +739,10 @@ def onetoall_kernel(data: RasterData, flags: Flags, cfg, solver=None, one_to_all
     if (not one_to_all) and inc is None and getattr(solver, "batch_all_to_one", False):
         batched = _all_to_one_batched_raster(G, comps, nodemap, newpoly, point_map, unique_point_map, uniq,
                                              rr, cc_, strengths, solver, o)
+    batched1 = {}
+    if one_to_all and inc is None and getattr(solver, "batch_one_to_all", False):
+        batched1 = _one_to_all_batched_raster(G, comps, nodemap, newpoly, point_map, unique_point_map, uniq,
+                                              rr, cc_, strengths, solver)
     for i, n in enumerate(uniq):
         pm, nm, npoly = point_map.copy(), nodemap, newpoly
         if inc is not None:
@@ -683,6 +757,18 @@ def onetoall_kernel(data: RasterData, flags: Flags, cfg, solver=None, one_to_all
             strength_map[rr - 1, cc_ - 1] = st[:, 1]
         if pm.sum() == n:                                           # no other focal node left
             res[i] = -1
+            continue
+        if i in batched1:                                           # one-to-all column of the grounded batch
+            outvolt, outcurr, val = batched1[i]
+            out.num_solves += 1
+            res[i] = -1 if np.isclose(val, 0) else val               # advanced.jl:252-263
+            if o.write_volt_maps:
+                out.voltmaps[n] = outvolt
+            if o.write_cur_maps or o.write_cum_cur_map_only:
+                out.curmaps[n] = outcurr
+            out.cum_curmap += outcurr
+            if out.max_curmap is not None:
+                out.max_curmap = np.maximum(out.max_curmap, outcurr)
             continue
         if i in batched:                                            # solved as a column of the batch
             outvolt, outcurr = batched[i]

@@ -44,6 +44,7 @@ class CUDASolver:
     mixed: bool = True               # fp64 + AMG: fp32 V-cycle inside fp64 CG
     superpose: bool = False          # pairwise driver: one solve per focal NODE, pairs by superposition
     batch_all_to_one: bool = False   # all-to-one: every iteration a column of ONE batch on one operator
+    batch_one_to_all: bool = False   # one-to-all: one solve per iteration on ONE grounded operator
 
     @property
     def dtype(self):

@@ -166,7 +166,7 @@ def test_onetoall_driver_matches_oracle(p, batched):
     points_rc = co.read_point_map("grid", pm, meta)
     data = cb.RasterData(cellmap, polymap, points_rc, None if strengths is None else strengths.copy(), inc)
     flags = cb.Flags.from_cfg(cfg)
-    got = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(batch_all_to_one=batched),
+    got = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(batch_all_to_one=batched, batch_one_to_all=batched),
                              four_neighbors=four, avg_res=False)
     assert got.resistances.shape == want.resistances.shape
     assert np.abs(got.resistances - want.resistances).max() < 1e-8 * max(1.0, np.abs(want.resistances).max())

@@ -64,6 +64,17 @@ def test_alltoone_driver_batched(golden, name):
     cases.check_onetoall(r, exp, flags)
 
 
+@pytest.mark.parametrize("name", [n for n in ONE_TO_ALL if n.startswith("oneToAll")])
+def test_onetoall_driver_batched(golden, name):
+    """CUDASolver(batch_one_to_all=True): the iterations of a component as columns of one batch on the
+    Laplacian with every focal row/column removed (block elimination of the live focal node)."""
+    data, flags, cfg, exp = cases.onetoall_problem(golden, name)
+    fl = co.cfg_flags(cfg)
+    r = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(batch_one_to_all=True),
+                           four_neighbors=fl["four_neighbors"], avg_res=fl["avg_res"])
+    cases.check_onetoall(r, exp, flags)
+
+
 def test_batching_is_transparent(golden):
     """cholmod_batch_size only changes how pairs are grouped (src/core.jl:448-452)."""
     a, exp = cases.run_raster_pairwise(golden, "sgVerify4", cb.CUDASolver(bs=1000))
