@@ -633,7 +633,14 @@ def _one_to_all_batched_raster(G, comps, nodemap, newpoly, point_map, unique_poi
             v[pl] = sval / denom
             v[Nidx] = v[pl] * W[:, c]
             cur = node_currents_host(a_local, v, None)
-            served[i] = (_scatter(v, lm), _scatter(cur, lm), v[pl] / sval)
+            # the reported value is read off the voltage RASTER at the source cell, through the local
+            # node map, exactly as the per-iteration path does (advanced.jl:252-263) -- with a NODATA
+            # cell inside a focal region the local numbering can differ from the matrix's
+            volt = np.zeros(lm.shape)
+            volt[lm != 0] = v[lm[lm != 0] - 1]
+            smap = np.where(unique_point_map == uniq[i], sval, 0.0)
+            val = (volt[smap != 0] / smap[smap != 0])[0]
+            served[i] = (_scatter(v, lm), _scatter(cur, lm), val)
     return served
 
 

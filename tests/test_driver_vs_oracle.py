@@ -226,3 +226,24 @@ def test_network_pairwise_driver_matches_oracle(p, superpose):
         assert gb.shape == wb.shape and np.abs(gb - wb).max(initial=0.0) < 1e-8
     assert np.abs(got.cum_node - want.cum_node).max() < 1e-8 * max(1.0, np.abs(want.cum_node).max())
     assert np.abs(got.cum_branch - want.cum_branch).max() < 1e-8 * max(1.0, np.abs(want.cum_branch).max())
+
+
+def test_onetoall_batched_reads_value_through_the_local_node_map():
+    """regression (found by the randomised comparison): a focal region whose first cell is NODATA --
+    the reported value is read off the voltage raster at the source cell, where the reference's
+    local node numbering differs from the matrix's; the batched path must reproduce that."""
+    N = -9999.0
+    g = np.array([[3.02968197, N, 3.79571608], [N, 1.90727603, N], [2.13672554, 1.50118691, N],
+                  [N, 1.14983282, 3.50826361], [N, 0.25732439, 1.38680231], [1.92996258, 2.58616864, 0.621780943]])
+    pm = np.array([[0, 0, 0], [0, 0, 1], [0, 0, 0], [0, 0, 0], [2, 0, 1], [3, 0, 0.]])
+    meta = np.array([3, 6, 0.0, 0.0, 1.0])
+    cfg = {"scenario": "one-to-all", "data_type": "raster", "habitat_map_is_resistances": "False",
+           "write_cur_maps": "True", "use_polygons": "False", "connect_four_neighbors_only": "True"}
+    inputs = {"habitat_file": ("grid", g, meta), "point_file": ("grid", pm, meta)}
+    want = co.raster_one_to_all(cfg, inputs)
+    cellmap, polymap, _, inc = co.load_raster_inputs(cfg, inputs)
+    data = cb.RasterData(cellmap, polymap, co.read_point_map("grid", pm, meta), None, inc)
+    for batched in (False, True):
+        got = cb.onetoall_kernel(data, cb.Flags.from_cfg(cfg), cfg, solver=cb.CUDASolver(batch_one_to_all=batched),
+                                 four_neighbors=True, avg_res=False)
+        assert np.abs(got.resistances - want.resistances).max() < 1e-9
