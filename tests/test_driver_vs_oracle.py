@@ -247,3 +247,36 @@ def test_onetoall_batched_reads_value_through_the_local_node_map():
         got = cb.onetoall_kernel(data, cb.Flags.from_cfg(cfg), cfg, solver=cb.CUDASolver(batch_one_to_all=batched),
                                  four_neighbors=True, avg_res=False)
         assert np.abs(got.resistances - want.resistances).max() < 1e-9
+
+
+@settings(max_examples=120, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(p=networks(), seed=st.integers(0, 2**31 - 1), policy=st.sampled_from(["keepall", "rmvsrc", "rmvgnd", "rmvall"]),
+       kind=st.sampled_from(["finite", "inf", "mixed"]))
+def test_network_advanced_driver_matches_oracle(p, seed, policy, kind):
+    raw, _ = p
+    rng = np.random.default_rng(seed)
+    i, j, v, _ = co.load_graph(raw, False)
+    G, cc = co.network_graph(i, j, v)
+    n = G.shape[0]
+    sources = np.where(rng.random(n) < 0.3, rng.uniform(0.5, 2.0, n), 0.0)
+    grounds = np.where(rng.random(n) < 0.3, rng.uniform(0.5, 2.0, n), 0.0)
+    if kind == "inf":
+        grounds = np.where(grounds != 0, np.inf, 0.0)
+    elif kind == "mixed":
+        grounds = np.where((grounds != 0) & (rng.random(n) < 0.5), np.inf, grounds)
+    s_o, g_o, f_o = co.resolve_conflicts(sources, grounds, policy)
+    s_p, g_p, f_p = cb.resolve_conflicts(sources, grounds, policy)
+    assert np.array_equal(s_o, s_p) and np.array_equal(g_o, g_p) and np.array_equal(f_o, f_p)
+    try:
+        want = co.advanced_kernel(G, cc, s_o, g_o, f_o)
+    except Exception:
+        return
+    got = cb.advanced_kernel(cb.AdvancedProblem(G, cc, s_p, g_p, f_p, None, None, None, cb.CUDASolver()),
+                             cb.Flags(is_raster=False, is_advanced=True))
+    scale = max(1.0, np.abs(want.voltages).max())
+    assert np.abs(got.voltages - want.voltages).max() < 1e-8 * scale
+    assert np.abs(got.node_currents - want.node_currents).max() < 1e-8 * max(1.0, np.abs(want.node_currents).max())
+    srt = lambda t: (lambda m: m[np.lexsort(m.T[::-1])])(np.column_stack([np.asarray(x, dtype=float) for x in t]))
+    wr, wc, wv = want.branch                               # the oracle keeps 0-based rows here
+    gb, wb = srt(got.branch), srt((np.asarray(wr) + 1, np.asarray(wc) + 1, wv))
+    assert gb.shape == wb.shape and np.abs(gb - wb).max(initial=0.0) < 1e-8 * max(1.0, np.abs(wb).max(initial=0.0))
