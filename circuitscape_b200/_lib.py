@@ -32,7 +32,8 @@ class B200Error(RuntimeError):
 class Opts(C.Structure):
     _fields_ = [("precond", C.c_int32), ("panel_width", C.c_int32), ("check_every", C.c_int32),
                 ("use_graph", C.c_int32), ("atol", C.c_double), ("resid_gate", C.c_double),
-                ("log_transform", C.c_int32), ("window", C.c_int32), ("mixed", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("log_transform", C.c_int32), ("window", C.c_int32), ("mixed", C.c_int32), ("setup", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class Stats(C.Structure):
@@ -57,6 +58,9 @@ _PROTOS = {
                                              C.POINTER(Opts), C.POINTER(_H), C.POINTER(C.c_int64),
                                              C.POINTER(C.c_int64)]),
     "cs_b200_get_csr": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_b200_level_info": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "cs_b200_level_csr": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_b200_get_dims": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cs_b200_destroy": (None, [_H]),
     "cs_b200_spmv": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double)]),

@@ -174,12 +174,16 @@ def _process_grid(cmap, cellmap, log_transform, set_null_to_nodata):
 # ---------------------------------------------------------------------------
 # pairwise driver
 # ---------------------------------------------------------------------------
-def single_ground_all_pairs(prob: GraphProblem, flags: Flags, cfg=None, log=True) -> PairwiseOutput:
+def single_ground_all_pairs(prob: GraphProblem, flags: Flags, cfg=None, log=True, sink=None) -> PairwiseOutput:
     """src/core.jl:70-72."""
-    return solve(prob, prob.solver, flags, cfg, log)
+    return solve(prob, prob.solver, flags, cfg, log, sink=sink)
 
 
-def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=True) -> PairwiseOutput:
+def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=True, sink=None) -> PairwiseOutput:
+    """`sink`: optional writer the per-pair results are handed to as each batch finishes -- the
+    reference writes every map inside `postprocess` and drops it (src/core.jl:655-683); without a
+    sink they are kept in the returned object (tests, small jobs).  A sink has the methods
+    `voltmap(key, grid)`, `curmap(key, grid)` (raster) and `network(key, comp, volt, cur, branch)`."""
     o = flags.outputflags
     P = len(prob.points)
     R = -np.ones((P, P))
@@ -195,6 +199,7 @@ def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=
     else:
         out.cum_node = np.zeros(prob.G.shape[0])
         out.cum_branch = np.zeros(len(prob.coords[0]))
+        branch_pos = _BranchIndex(prob.coords)
     G = sp.csr_matrix(prob.G)
     points = np.asarray(prob.points)
     ids = np.asarray(prob.user_points)
@@ -219,11 +224,17 @@ def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=
         dst = np.array([local_of[d] for _, d, _ in solves])
         weight = np.array([len(f) for _, _, f in solves], dtype=np.float64)
         need_curr = not shortcut                       # postprocess always builds the current map
-        per_pair_volt = o.write_volt_maps or shortcut or (not raster and not shortcut)
+        per_pair_volt = o.write_volt_maps or (not raster and not shortcut)   # network branch currents need v
         per_pair_curr = need_curr and ((o.write_cur_maps and not o.write_cum_cur_map_only) or not raster)
         local_nodemap = construct_local_node_map(prob.nodemap, comp, prob.polymap) if raster and not shortcut else None
-        with S.construct_cholesky_factor(matrix, solver, log_transform=o.log_transform_maps) as factor:
+        # only raster maps are log-transformed (src/out.jl:96 process_grid!); the network branch of
+        # write_cur_maps accumulates raw node currents (src/out.jl:48-88)
+        with S.construct_cholesky_factor(matrix, solver, log_transform=bool(o.log_transform_maps and raster)) as factor:
             bs = max(1, int(solver.bs))
+            if shortcut:
+                inside = np.nonzero(np.isin(points, comp) & (points != 0))[0]
+                focal_rows = np.unique(local_of[points[inside]])
+                focal_col = {int(r): i for i, r in enumerate(focal_rows)}
 
             def batches():
                 if getattr(solver, "superpose", False) and not shortcut and len(solves) > 1:
@@ -236,6 +247,14 @@ def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=
                     return
                 for st in range(0, len(solves), bs):                            # src/core.jl:448-452
                     sl = slice(st, min(st + bs, len(solves)))
+                    if shortcut:
+                        # only the voltages at the focal nodes are used (update_voltmatrix!,
+                        # src/core.jl:685-703): probe rows instead of n x k voltages over PCIe
+                        res = factor.solve_sources([([s_, d_], [-1.0, 1.0]) for s_, d_ in zip(src[sl], dst[sl])],
+                                                   ref=src[sl], probe=focal_rows)
+                        res["R"] = np.array([res["probe_volt"][c, focal_col[d_]] for c, d_ in enumerate(dst[sl])])
+                        yield sl, res
+                        continue
                     yield sl, factor.solve_pairs(src[sl], dst[sl], weight[sl], want_volt=per_pair_volt,
                                                  want_curr=per_pair_curr, accumulate=need_curr)
 
@@ -245,28 +264,43 @@ def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=
                 out.iterations += int(res["iters"].sum())
                 for col, (s, d, fan) in enumerate(solves[sl]):
                     r = float(res["R"][col])
-                    v = res["volt"][:, col].astype(np.float64) if res["volt"] is not None else None
-                    cur = res["curr"][:, col].astype(np.float64) if res["curr"] is not None else None
+                    v = res["volt"][:, col].astype(np.float64) if res.get("volt") is not None else None
+                    cur = res["curr"][:, col].astype(np.float64) if res.get("curr") is not None else None
+                    br = _branch_currents(matrix, v, comp) if not raster and not shortcut else None
                     for ci, cj in fan:
                         R[ci, cj] = R[cj, ci] = r
                         key = (int(ids[ci]), int(ids[cj]))
                         if shortcut:                                             # src/core.jl:685-703
-                            inside = np.nonzero(np.isin(points, comp) & (points != 0))[0]
+                            pv = res["probe_volt"][col]
                             for i in inside[inside >= 1]:
-                                voltmatrix[i, cj] = 1.0 - v[local_of[points[i]]] / r
+                                voltmatrix[i, cj] = 1.0 - float(pv[focal_col[int(local_of[points[i]])]]) / r
                             continue
                         if raster:
                             if o.write_volt_maps:
-                                out.voltmaps[key] = _process_grid(_scatter(v, local_nodemap), prob.cellmap,
-                                                                  False, o.set_null_voltages_to_nodata)
+                                vm = _process_grid(_scatter(v, local_nodemap), prob.cellmap,
+                                                   False, o.set_null_voltages_to_nodata)
+                                if sink is not None:
+                                    sink.voltmap(key, vm)
+                                else:
+                                    out.voltmaps[key] = vm
                             if per_pair_curr:
-                                out.curmaps[key] = _process_grid(_scatter(cur, local_nodemap), prob.cellmap,
-                                                                 o.log_transform_maps,
-                                                                 o.set_null_currents_to_nodata)
+                                cm = _process_grid(_scatter(cur, local_nodemap), prob.cellmap,
+                                                   o.log_transform_maps, o.set_null_currents_to_nodata)
+                                if sink is not None:
+                                    sink.curmap(key, cm)
+                                else:
+                                    out.curmaps[key] = cm
                         else:
-                            out.voltmaps[key] = (comp, v)
-                            out.curmaps[key] = (comp, cur)
-                            out.branch[key] = _branch_currents(matrix, v, comp)
+                            # every id combination is post-processed on its own (src/core.jl:235-249):
+                            # its branch currents go into the cumulative vector once each
+                            branch_pos.add(out.cum_branch, br)
+                            if sink is not None:
+                                sink.network(key, comp, v if o.write_volt_maps else None, cur, br)
+                            else:
+                                if o.write_volt_maps:
+                                    out.voltmaps[key] = (comp, v)
+                                out.curmaps[key] = (comp, cur)
+                                out.branch[key] = br
             if need_curr:
                 cum, mx = factor.read_currents(want_max=True)
                 if raster:
@@ -287,7 +321,6 @@ def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=
                         out.max_curmap = np.maximum(out.max_curmap, mmap)
                 else:
                     out.cum_node[rows] += cum
-                    _accumulate_branches(out, prob.coords)
         if shortcut:
             anchor = int(np.nonzero(points == csub[0])[0][0])
             _update_shortcut_resistances(anchor, voltmatrix, shortcut_res, R, points, comp)
@@ -309,27 +342,53 @@ def solve(prob: GraphProblem, solver: S.CUDASolver, flags: Flags, cfg=None, log=
 def _branch_currents(matrix, v, comp):
     """Network mode branch currents |G_ij| |v_i - v_j| over the stored upper triangle
     with the 1e-8 relative zeroing (src/out.jl:154-158, 250-290); host side, network
-    graphs only."""
+    graphs only.  Rows come in the order `_convert_to_3col` walks the CSC branch matrix
+    (column-major: sorted by column, then row), so written files match the reference's."""
     coo = sp.triu(sp.csr_matrix(matrix), k=1).tocoo()
-    b = np.abs(coo.data) * (v[coo.row] - v[coo.col])
+    order = np.lexsort((coo.row, coo.col))
+    row, col, data = coo.row[order], coo.col[order], coo.data[order]
+    b = np.abs(data) * (v[row] - v[col])
     if len(b):
         mx = b.max()
         with np.errstate(divide="ignore", invalid="ignore"):
             b = np.where(np.abs(b / mx) < 1e-8, 0.0, b)
-    return comp[coo.row], comp[coo.col], np.abs(b)
+    return comp[row], comp[col], np.abs(b)
 
 
-def _accumulate_branches(out, coords):
-    pos = {}
-    for k, (a, b) in enumerate(zip(coords[0], coords[1])):
-        pos.setdefault((int(a), int(b)), k)
-    out.cum_branch[:] = 0.0
-    for (gr, gc, val) in out.branch.values():
-        for a, b, x in zip(gr, gc, val):
-            k = pos.get((int(a), int(b)))
-            if k is None:
-                k = pos.get((int(b), int(a)))
-            out.cum_branch[k] += x
+class _BranchIndex:
+    """Position of every graph edge in `coords` (the cumulative branch vector's order,
+    src/utils.jl:132-142) by a sorted key table instead of the reference's linear `findfirst`
+    per branch (src/out.jl:65-84).  An edge that is not in `coords` raises, like the reference's
+    `cbc[nothing]`."""
+
+    def __init__(self, coords):
+        a = np.asarray(coords[0], dtype=np.int64)
+        b = np.asarray(coords[1], dtype=np.int64)
+        self.base = int(max(a.max(initial=0), b.max(initial=0))) + 1
+        key = a * self.base + b
+        # findfirst semantics: the first occurrence of a repeated edge wins
+        self.order = np.argsort(key, kind="stable")
+        self.keys = key[self.order]
+
+    def _find(self, a, b):
+        key = a * self.base + b
+        pos = np.searchsorted(self.keys, key, side="left")
+        ok = (pos < len(self.keys))
+        ok[ok] = self.keys[pos[ok]] == key[ok]
+        return np.where(ok, self.order[np.minimum(pos, len(self.keys) - 1)], -1)
+
+    def add(self, cum, branch):
+        gr, gc, val = branch
+        gr = np.asarray(gr, dtype=np.int64)
+        gc = np.asarray(gc, dtype=np.int64)
+        k = self._find(gr, gc)
+        miss = k < 0
+        if miss.any():
+            k[miss] = self._find(gc[miss], gr[miss])
+        if (k < 0).any():
+            i = int(np.nonzero(k < 0)[0][0])
+            raise KeyError(f"branch ({int(gr[i])}, {int(gc[i])}) is not an edge of the graph")
+        np.add.at(cum, k, val)
 
 
 def _update_shortcut_resistances(anchor, voltmatrix, shortcut, resistances, points, comp):

@@ -205,6 +205,76 @@ inline int aggregate(const Csr& a, std::vector<int>& agg) {
   return nagg;
 }
 
+
+// ---- MIS(2) aggregation: the PARALLEL scheme the device setup runs (setup_device.cu), restated
+// sequentially with the same synchronous rounds, the same hash and the same tie rules, so that
+// host and device produce identical aggregates (tests compare them).
+//   roots      = a maximal independent set of the distance-2 strength graph (Bell/Dalton/Olson):
+//                every undecided node carries the key (state, hash(i), i); after two rounds of
+//                neighbourhood max-propagation a node whose own key came back is a root, a node
+//                that saw a root's key is out
+//   aggregates = root + its neighbours (strongest root wins) + distance-2 nodes (strongest
+//                already-aggregated neighbour wins); numbered by root id order
+inline uint32_t mis_hash(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+inline uint64_t mis_key(uint32_t state, uint32_t i) {
+  return ((uint64_t)state << 62) | ((uint64_t)(mis_hash(i) & 0x3fffffffU) << 32) | (uint64_t)i;
+}
+inline int aggregate_mis2(const Csr& a, std::vector<int>& agg) {
+  const int64_t n = a.nrows;
+  enum : uint32_t { OUT = 0, UND = 1, IN = 2 };
+  std::vector<uint64_t> key(n), t1(n), t2(n);
+  std::vector<char> isolated(n, 0);
+  int64_t undecided = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    bool any = false;
+    for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j)
+      if (a.idx[j] != i && a.val[j] != 0.0) { any = true; break; }
+    isolated[i] = !any;
+    key[i] = mis_key(any ? UND : OUT, (uint32_t)i);
+    undecided += any;
+  }
+  auto nbmax = [&](const std::vector<uint64_t>& in, std::vector<uint64_t>& out) {
+    for (int64_t i = 0; i < n; ++i) {
+      uint64_t m = in[i];
+      for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j)
+        if (a.idx[j] != i && a.val[j] != 0.0) m = std::max(m, in[a.idx[j]]);
+      out[i] = m;
+    }
+  };
+  while (undecided > 0) {
+    nbmax(key, t1);
+    nbmax(t1, t2);
+    for (int64_t i = 0; i < n; ++i) {
+      if ((key[i] >> 62) != UND) continue;
+      if (t2[i] == key[i]) { key[i] = mis_key(IN, (uint32_t)i); --undecided; }
+      else if ((t2[i] >> 62) == IN) { key[i] = mis_key(OUT, (uint32_t)i); --undecided; }
+    }
+  }
+  agg.assign(n, -1);
+  int nagg = 0;
+  for (int64_t i = 0; i < n; ++i) if ((key[i] >> 62) == IN) agg[i] = nagg++;
+  for (int pass = 0; pass < 2; ++pass) {
+    const std::vector<int> snap(agg);
+    for (int64_t i = 0; i < n; ++i) {
+      if (snap[i] >= 0 || isolated[i]) continue;
+      double best = -1.0;
+      int pick = -1;
+      for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j) {
+        const int c = a.idx[j];
+        if (c == i || a.val[j] == 0.0 || snap[c] < 0) continue;
+        if (pass == 0 && (key[c] >> 62) != IN) continue;       // pass 0: roots only
+        const double w = std::fabs(a.val[j]);
+        if (w > best) { best = w; pick = snap[c]; }
+      }
+      if (pick >= 0) agg[i] = pick;
+    }
+  }
+  return nagg;
+}
+
 // dense symmetric pseudo-inverse by cyclic Jacobi rotations (n <= a few hundred)
 inline std::vector<double> dense_pinv(const Csr& a) {
   const int n = (int)a.nrows;
@@ -324,7 +394,7 @@ inline void diag_and_rho(const Csr& a, std::vector<double>& dinv, double& rho) {
   rho = lam > 0.0 ? std::min(rho_inf, std::max(lam, 0.7 * rho_inf)) : rho_inf;
 }
 
-inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 200) {
+inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 200, bool mis2 = false) {
   Hierarchy h;
   h.levels.emplace_back();
   h.levels.back().A = std::move(a0);
@@ -336,7 +406,7 @@ inline Hierarchy build_hierarchy(Csr a0, int max_levels = 12, int max_coarse = 2
     const int64_t n = lv.A.nrows;
     if ((int)h.levels.size() >= max_levels || n <= max_coarse) break;
     std::vector<int> agg;
-    const int nagg = aggregate(lv.A, agg);
+    const int nagg = mis2 ? aggregate_mis2(lv.A, agg) : aggregate(lv.A, agg);
     if (nagg <= 0 || nagg >= n) break;
     std::vector<double> cnt(nagg, 0.0);
     for (int64_t i = 0; i < n; ++i) if (agg[i] >= 0) cnt[agg[i]] += 1.0;

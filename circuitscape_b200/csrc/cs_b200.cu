@@ -20,6 +20,7 @@
 #include "win_host.hpp"
 #include "kernels.cuh"
 #include "raster_assembly.cuh"
+#include "setup_device.hpp"
 
 using namespace csb;
 
@@ -372,16 +373,9 @@ int setup_amg(cs_b200_handle* h, const std::vector<int>& rp, const std::vector<i
   return CS_B200_OK;
 }
 
+// panels, 1/diag, current vectors, control block: what every handle needs whatever built its operators
 template <typename T>
-int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std::vector<int>* h_colidx,
-                 const T* h_vals) {
-  std::vector<int> bstart;
-  build_row_blocks(h_rowptr, h->n, bstart);
-  h->nblocks = (int)bstart.size() - 1;
-  CK(h, cudaMalloc(&h->d_bstart, bstart.size() * sizeof(int)));
-  CK(h, cudaMemcpyAsync(h->d_bstart, bstart.data(), bstart.size() * sizeof(int),
-                        cudaMemcpyHostToDevice, h->stream));
-  h->A0 = DevCsr{h->d_rowptr, h->d_colidx, h->d_vals, h->d_bstart, h->nblocks, (int)h->n, h->nnz, 1};
+int alloc_common(cs_b200_handle* h) {
   const size_t pe = (size_t)h->n_pad * h->ktmax;
   void** bufs[] = {&h->X, &h->R, &h->P, &h->AP, &h->B, &h->stage};
   for (void** b : bufs) {
@@ -399,6 +393,21 @@ int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std:
   k_dinv<T><<<std::min<int64_t>((h->n_pad + 255) / 256, 4096), 256, 0, h->stream>>>(
       (int)h->n, (int)h->n_pad, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (T*)h->d_dinv);
   CK(h, cudaGetLastError());
+  return CS_B200_OK;
+}
+
+template <typename T>
+int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std::vector<int>* h_colidx,
+                 const T* h_vals) {
+  std::vector<int> bstart;
+  build_row_blocks(h_rowptr, h->n, bstart);
+  h->nblocks = (int)bstart.size() - 1;
+  CK(h, cudaMalloc(&h->d_bstart, bstart.size() * sizeof(int)));
+  CK(h, cudaMemcpyAsync(h->d_bstart, bstart.data(), bstart.size() * sizeof(int),
+                        cudaMemcpyHostToDevice, h->stream));
+  h->A0 = DevCsr{h->d_rowptr, h->d_colidx, h->d_vals, h->d_bstart, h->nblocks, (int)h->n, h->nnz, 1};
+  int rc0 = alloc_common<T>(h);
+  if (rc0) return rc0;
   CK(h, cudaStreamSynchronize(h->stream));
   std::vector<int> ci_local;
   std::vector<T> v_local;
@@ -424,6 +433,222 @@ int finish_setup(cs_b200_handle* h, const std::vector<int>& h_rowptr, const std:
     int rc = setup_amg<T>(h, h_rowptr, *h_colidx, h_vals);
     if (rc) return rc;
   }
+  return cs_b200_reset_currents(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side setup (setup_device.cu): row blocks, windowed records and the multigrid hierarchy are
+// built on the GPU from the resident CSR; only the ordered aggregation seed pass runs on the host
+// ---------------------------------------------------------------------------------------------
+int rc_dev(cs_b200_handle* h, int rc) {   // csb_dev codes -> cs_b200 status (h->err already set)
+  (void)h;
+  if (rc == 0) return CS_B200_OK;
+  return rc == -5 ? CS_B200_ERR_UNSUPPORTED : CS_B200_ERR_CUDA;
+}
+
+// plain-kernel row blocks of a device CSR (the partition build_row_blocks computes on the host)
+int device_row_blocks(cs_b200_handle* h, DevCsr& d, int max_rows) {
+  int* bs = nullptr;
+  int nb = 0;
+  int rc = csb_dev::row_blocks(h->stream, d.rowptr, d.nrows, max_rows, NNZ_CAP, &bs, &nb, h->err);
+  if (rc) return rc_dev(h, rc);
+  d.bstart = bs;
+  d.nblocks = nb;
+  return CS_B200_OK;
+}
+
+template <typename T>
+int device_windows(cs_b200_handle* h, DevCsr& d, int64_t ncols_pad, const T* d_dinv) {
+  csb_dev::DWin w;
+  int rc = csb_dev::build_windowed<T>(h->stream, d.rowptr, d.colidx, (const T*)d.vals, d.nrows, ncols_pad,
+                                      d.lpr == 4 ? W_WCAP_WIDE : W_WCAP, d_dinv, w, h->err);
+  if (rc) return rc_dev(h, rc);
+  d.has_dinv = d_dinv != nullptr ? 1 : 0;
+  d.win_blocks = w.windowed_blocks;
+  d.win_nblocks = w.nblocks;
+  d.win_meta = reinterpret_cast<WinMeta*>(w.meta);
+  d.blob = w.blob;
+  return CS_B200_OK;
+}
+
+// take over a hierarchy operator as a device CSR of TV: the index arrays move (or are duplicated when
+// the source is the handle's own matrix), the fp64 values move or are converted
+template <typename TV>
+int adopt_csr(cs_b200_handle* h, csb_dev::DCsr& src, bool duplicate, DevCsr& d, bool windowed, const TV* d_dinv) {
+  d.nrows = (int)src.nrows;
+  d.nnz = src.nnz;
+  d.lpr = (src.nrows > 0 && (double)d.nnz / (double)src.nrows >= 20.0) ? 4 : 1;
+  const size_t np = (size_t)src.nrows + 1, ne = std::max<size_t>(1, (size_t)src.nnz);
+  if (duplicate) {
+    CK(h, cudaMalloc(&d.rowptr, np * sizeof(int)));
+    CK(h, cudaMalloc(&d.colidx, ne * sizeof(int)));
+    CK(h, cudaMemcpyAsync(d.rowptr, src.ptr, np * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(d.colidx, src.idx, (size_t)src.nnz * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    d.rowptr = src.ptr; src.ptr = nullptr;
+    d.colidx = src.idx; src.idx = nullptr;
+  }
+  if (sizeof(TV) == 8 && !duplicate) {
+    d.vals = src.val; src.val = nullptr;
+  } else {
+    CK(h, cudaMalloc(&d.vals, ne * sizeof(TV)));
+    if (sizeof(TV) == 8) {
+      CK(h, cudaMemcpyAsync(d.vals, src.val, (size_t)src.nnz * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    } else if (csb_dev::convert_values(h->stream, src.val, (float*)d.vals, src.nnz)) {
+      return set_err(h, CS_B200_ERR_CUDA, "value conversion launch failed");
+    }
+    if (!duplicate) {
+      CK(h, cudaStreamSynchronize(h->stream));
+      cudaFree(src.val); src.val = nullptr;
+    }
+  }
+  // small operators (coarse levels): shrink the row blocks so that >= 4 CTAs per SM exist
+  const int unit = d.lpr == 4 ? 8 : 32;
+  int max_rows = (int)((src.nrows + 4 * h->num_sms - 1) / (4 * h->num_sms));
+  max_rows = std::min(NT, std::max(unit, (max_rows + unit - 1) / unit * unit));
+  int rc = device_row_blocks(h, d, max_rows);
+  if (rc) return rc;
+  if (h->opts.window >= 0 && windowed) {
+    const int64_t ncols_pad = (src.ncols + 3) / 4 * 4;
+    return device_windows<TV>(h, d, ncols_pad, d_dinv);
+  }
+  return CS_B200_OK;
+}
+
+template <typename TV>
+int adopt_levels(cs_b200_handle* h, csb_dev::DHierarchy& hier, std::vector<DevLevel>& lv, bool own0) {
+  const int nl = (int)hier.levels.size();
+  lv.resize(nl);
+  for (int l = 0; l < nl; ++l) {
+    csb_dev::DLevel& hl = hier.levels[l];
+    DevLevel& L = lv[l];
+    L.n = hl.A.nrows;
+    L.n_pad = (L.n + 3) / 4 * 4;
+    L.omega = hl.omega;
+    if (l == 0 && !own0) {
+      L.A = h->A0;  // alias, not owned
+      L.dinv = h->d_dinv;
+    } else {
+      CK(h, cudaMalloc(&L.dinv, (size_t)L.n_pad * sizeof(TV)));
+      CK(h, cudaMemsetAsync(L.dinv, 0, (size_t)L.n_pad * sizeof(TV), h->stream));
+      if (sizeof(TV) == 8) {
+        CK(h, cudaMemcpyAsync(L.dinv, hl.dinv, (size_t)L.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      } else if (csb_dev::convert_values(h->stream, hl.dinv, (float*)L.dinv, L.n)) {
+        return set_err(h, CS_B200_ERR_CUDA, "dinv conversion launch failed");
+      }
+      const bool win = h->opts.window > 0 || (L.n >= 20000 && (win_mask() & (l == 0 ? 1 : 2)));
+      int rc = adopt_csr<TV>(h, hl.A, l == 0, L.A, win, (const TV*)L.dinv);
+      if (rc) return rc;
+      if (l > 0) {
+        const size_t pe = (size_t)L.n_pad * h->ktmax * sizeof(TV);
+        void** bufs[] = {&L.x, &L.b, &L.t, &L.y};
+        for (void** bp : bufs) {
+          CK(h, cudaMalloc(bp, pe));
+          CK(h, cudaMemsetAsync(*bp, 0, pe, h->stream));
+        }
+      }
+    }
+    if (l + 1 < nl) {
+      int rc = adopt_csr<TV>(h, hl.P, false, L.P, L.n >= 20000 && (win_mask() & 4), (const TV*)nullptr);
+      if (rc) return rc;
+      rc = adopt_csr<TV>(h, hl.R, false, L.R, L.n >= 20000 && (win_mask() & 8), (const TV*)nullptr);
+      if (rc) return rc;
+    }
+  }
+  return CS_B200_OK;
+}
+
+template <typename T>
+int setup_amg_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job) {
+  const bool verbose = std::getenv("CS_B200_VERBOSE") != nullptr;
+  csb_dev::DCsr a0;
+  a0.nrows = a0.ncols = h->n;
+  a0.nnz = h->nnz;
+  a0.ptr = h->d_rowptr;
+  a0.idx = h->d_colidx;
+  double* tmp64 = nullptr;
+  if (sizeof(T) == 8) {
+    a0.val = (double*)h->d_vals;
+  } else {   // the hierarchy is built in fp64 whatever the handle computes in
+    cudaError_t e = cudaMalloc(&tmp64, std::max<size_t>(1, (size_t)h->nnz) * sizeof(double));
+    if (e != cudaSuccess) {
+      csb_dev::seed_discard(job);
+      return set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (fp64 copy of the matrix)", cudaGetErrorString(e));
+    }
+    csb_dev::convert_values(h->stream, (const float*)h->d_vals, tmp64, h->nnz);
+    a0.val = tmp64;
+  }
+  Tick tick;
+  csb_dev::DHierarchy hier;
+  int rc = csb_dev::build_hierarchy(h->stream, a0, hp, job, 12, 200, hier, h->err, verbose);
+  auto done = [&](int code) {
+    cudaStreamSynchronize(h->stream);
+    csb_dev::free_hierarchy(hier);
+    cudaFree(tmp64);
+    return code;
+  };
+  if (rc) return done(rc_dev(h, rc));
+  tick("device hierarchy");
+  h->amg_opc = hier.operator_complexity;
+  const int nl = (int)hier.levels.size();
+  h->mixed = nl > 1 && sizeof(T) == 8 && h->opts.mixed >= 0;
+  if (h->mixed) {
+    rc = adopt_levels<float>(h, hier, h->lv32, true);
+    if (rc) return done(rc);
+    h->lv.resize(nl);
+    for (int l = 0; l < nl; ++l) { h->lv[l].n = hier.levels[l].A.nrows; h->lv[l].omega = hier.levels[l].omega; }
+    h->lv[0].A = h->A0;
+    h->lv[0].dinv = h->d_dinv;
+    const size_t pe = (size_t)h->n_pad * h->ktmax * sizeof(float);
+    void** bufs[] = {&h->R32, &h->X32, &h->T32, &h->Z32};
+    for (void** bp : bufs) {
+      cudaError_t e = cudaMalloc(bp, pe);
+      if (e == cudaSuccess) e = cudaMemsetAsync(*bp, 0, pe, h->stream);
+      if (e != cudaSuccess) return done(set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (fp32 panels)", cudaGetErrorString(e)));
+    }
+  } else {
+    rc = adopt_levels<T>(h, hier, h->lv, false);
+    if (rc) return done(rc);
+    const size_t pe = (size_t)h->n_pad * h->ktmax * sizeof(T);
+    cudaError_t e = cudaMalloc(&h->Z, pe);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->Z, 0, pe, h->stream);
+    if (e != cudaSuccess) return done(set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (Z panel)", cudaGetErrorString(e)));
+  }
+  tick("levels: row blocks + windows");
+  const size_t nc = (size_t)hier.levels.back().A.nrows;
+  if (hier.coarse_pinv.size() == nc * nc && nc > 0) {
+    cudaError_t e = cudaMalloc(&h->d_pinv, nc * nc * sizeof(double));
+    if (e == cudaSuccess) e = h2d(h, h->d_pinv, hier.coarse_pinv.data(), nc * nc * sizeof(double));
+    if (e != cudaSuccess) return done(set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (coarse pseudo-inverse)", cudaGetErrorString(e)));
+  }
+  h->amg = nl > 1;
+  return done(CS_B200_OK);
+}
+
+template <typename T>
+int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job) {
+  h->A0 = DevCsr{h->d_rowptr, h->d_colidx, h->d_vals, nullptr, 0, (int)h->n, h->nnz, 1};
+  int rc = device_row_blocks(h, h->A0, NT);
+  if (rc) { csb_dev::seed_discard(job); return rc; }
+  h->d_bstart = h->A0.bstart;
+  h->nblocks = h->A0.nblocks;
+  rc = alloc_common<T>(h);
+  if (rc) { csb_dev::seed_discard(job); return rc; }
+  const bool want_win = h->opts.window >= 0 && (h->opts.window > 0 || h->n >= 20000) && (win_mask() & 1);
+  const bool want_amg = h->opts.precond == CS_B200_PRECOND_AMG;
+  Tick tick;
+  if (want_win) {
+    rc = device_windows<T>(h, h->A0, h->n_pad, (const T*)h->d_dinv);
+    if (rc) { csb_dev::seed_discard(job); return rc; }
+    tick("finest operator: windows");
+  }
+  if (want_amg) {
+    rc = setup_amg_device<T>(h, hp, job);
+    if (rc) return rc;
+  } else {
+    csb_dev::seed_discard(job);
+  }
+  csb_dev::trim_pool(h->device);
   return cs_b200_reset_currents(h);
 }
 
@@ -1402,6 +1627,62 @@ int cs_b200_create(int64_t n, int64_t nnz, const void* rowptr, const void* colid
   if (rc) { g_create_error = h->err; cs_b200_destroy(h); return rc; }
   auto fail = [&](int code) { g_create_error = h->err; cs_b200_destroy(h); return code; };
   cudaEventRecord(h->ev0, h->stream);
+  const size_t es = h->esize();
+#define CKC(call)                                                                              \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (%s)", cudaGetErrorString(_e), #call);       \
+      return fail(CS_B200_ERR_CUDA);                                                           \
+    }                                                                                          \
+  } while (0)
+  if (h->opts.setup != 1) {
+    // ---- device-side setup: raw index arrays go up as they are and are narrowed on the GPU; the
+    // ordered aggregation seed pass starts right away on a helper thread (it only reads the
+    // caller's arrays) and overlaps the upload
+    const int64_t first = index_bits == 64 ? ((const int64_t*)rowptr)[0] : (int64_t)((const int32_t*)rowptr)[0];
+    const int64_t last = index_bits == 64 ? ((const int64_t*)rowptr)[n] : (int64_t)((const int32_t*)rowptr)[n];
+    if (first - index_base != 0 || last - index_base != nnz) {
+      set_err(h, CS_B200_ERR_ARG, "rowptr does not span [0, nnz] (got %lld..%lld)", (long long)(first - index_base),
+              (long long)(last - index_base));
+      return fail(CS_B200_ERR_ARG);
+    }
+    const csb_dev::HostPattern hp{rowptr, colidx, index_bits, index_base};
+    csb_dev::SeedJob* job = nullptr;
+    if (h->opts.precond == CS_B200_PRECOND_AMG && n > 200) job = csb_dev::seed_start(n, hp);
+    auto fail_job = [&](int code) { csb_dev::seed_discard(job); job = nullptr; return fail(code); };
+#define CKJ(call)                                                                              \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (%s)", cudaGetErrorString(_e), #call);       \
+      return fail_job(CS_B200_ERR_CUDA);                                                       \
+    }                                                                                          \
+  } while (0)
+    CKJ(cudaMalloc(&h->d_rowptr, (size_t)(n + 1) * sizeof(int)));
+    CKJ(cudaMalloc(&h->d_colidx, std::max<size_t>(1, (size_t)nnz) * sizeof(int)));
+    CKJ(cudaMalloc(&h->d_vals, std::max<size_t>(1, (size_t)nnz) * es));
+    if (index_bits == 32 && index_base == 0) {
+      CKJ(cudaMemcpyAsync(h->d_rowptr, rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      CKJ(cudaMemcpyAsync(h->d_colidx, colidx, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    } else {
+      const size_t ib = index_bits / 8;
+      void* raw = nullptr;
+      CKJ(cudaMalloc(&raw, std::max<size_t>((size_t)(n + 1), (size_t)nnz) * ib));
+      cudaError_t e = cudaMemcpyAsync(raw, rowptr, (size_t)(n + 1) * ib, cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) e = (cudaError_t)csb_dev::narrow_indices(h->stream, raw, index_bits, index_base, n + 1, h->d_rowptr);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(raw, colidx, (size_t)nnz * ib, cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) e = (cudaError_t)csb_dev::narrow_indices(h->stream, raw, index_bits, index_base, nnz, h->d_colidx);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      cudaFree(raw);
+      CKJ(e);
+    }
+    CKJ(cudaMemcpyAsync(h->d_vals, vals, (size_t)nnz * es, cudaMemcpyHostToDevice, h->stream));
+#undef CKJ
+    { Tick tick; if (tick.on) { cudaStreamSynchronize(h->stream); tick("upload (narrowed on device)"); } }
+    rc = dtype == CS_B200_F64 ? finish_setup_device<double>(h, hp, job) : finish_setup_device<float>(h, hp, job);
+    if (rc) return fail(rc);
+  } else {
   std::vector<int> rp, ci;
   if (index_bits == 64) {
     narrow_indices((const int64_t*)rowptr, n + 1, index_base, rp);
@@ -1414,15 +1695,6 @@ int cs_b200_create(int64_t n, int64_t nnz, const void* rowptr, const void* colid
     set_err(h, CS_B200_ERR_ARG, "rowptr does not span [0, nnz] (got %d..%d)", rp[0], rp[n]);
     return fail(CS_B200_ERR_ARG);
   }
-  const size_t es = h->esize();
-#define CKC(call)                                                                              \
-  do {                                                                                         \
-    cudaError_t _e = (call);                                                                   \
-    if (_e != cudaSuccess) {                                                                   \
-      set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (%s)", cudaGetErrorString(_e), #call);       \
-      return fail(CS_B200_ERR_CUDA);                                                           \
-    }                                                                                          \
-  } while (0)
   CKC(cudaMalloc(&h->d_rowptr, (size_t)(n + 1) * sizeof(int)));
   CKC(cudaMalloc(&h->d_colidx, std::max<size_t>(1, (size_t)nnz) * sizeof(int)));
   CKC(cudaMalloc(&h->d_vals, std::max<size_t>(1, (size_t)nnz) * es));
@@ -1432,6 +1704,7 @@ int cs_b200_create(int64_t n, int64_t nnz, const void* rowptr, const void* colid
   rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, &ci, (const double*)vals)
                             : finish_setup<float>(h, rp, &ci, (const float*)vals);
   if (rc) return fail(rc);
+  }
   cudaEventRecord(h->ev1, h->stream);
   cudaEventSynchronize(h->ev1);
   float ms = 0;
@@ -1458,14 +1731,19 @@ int cs_b200_create_from_device(int64_t n, int64_t nnz, const int32_t* d_rowptr,
   h->d_rowptr = const_cast<int*>(d_rowptr);
   h->d_colidx = const_cast<int*>(d_colidx);
   h->d_vals = const_cast<void*>(d_vals);
-  std::vector<int> rp(n + 1);
-  cudaError_t e = cudaMemcpy(rp.data(), d_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) {
-    set_err(h, CS_B200_ERR_CUDA, "CUDA error %s reading rowptr", cudaGetErrorString(e));
-    g_create_error = h->err; cs_b200_destroy(h); return CS_B200_ERR_CUDA;
+  if (h->opts.setup != 1) {
+    const csb_dev::HostPattern hp{};
+    rc = dtype == CS_B200_F64 ? finish_setup_device<double>(h, hp, nullptr) : finish_setup_device<float>(h, hp, nullptr);
+  } else {
+    std::vector<int> rp(n + 1);
+    cudaError_t e = cudaMemcpy(rp.data(), d_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      set_err(h, CS_B200_ERR_CUDA, "CUDA error %s reading rowptr", cudaGetErrorString(e));
+      g_create_error = h->err; cs_b200_destroy(h); return CS_B200_ERR_CUDA;
+    }
+    rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, nullptr, (const double*)nullptr)
+                              : finish_setup<float>(h, rp, nullptr, (const float*)nullptr);
   }
-  rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, nullptr, (const double*)nullptr)
-                            : finish_setup<float>(h, rp, nullptr, (const float*)nullptr);
   if (rc) { g_create_error = h->err; cs_b200_destroy(h); return rc; }
   cudaEventRecord(h->ev1, h->stream);
   cudaEventSynchronize(h->ev1);
@@ -1497,9 +1775,15 @@ int cs_b200_create_from_raster(int64_t nrows, int64_t ncols, const void* g, int 
   rc = dtype == CS_B200_F64
            ? assemble_raster<double>(h, nrows, ncols, (const double*)g, four_neighbors ? 1 : 0, avg_res ? 1 : 0, rp)
            : assemble_raster<float>(h, nrows, ncols, (const float*)g, four_neighbors ? 1 : 0, avg_res ? 1 : 0, rp);
-  if (!rc)
-    rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, nullptr, (const double*)nullptr)
-                              : finish_setup<float>(h, rp, nullptr, (const float*)nullptr);
+  if (!rc) {
+    if (h->opts.setup != 1) {
+      const csb_dev::HostPattern hp{};
+      rc = dtype == CS_B200_F64 ? finish_setup_device<double>(h, hp, nullptr) : finish_setup_device<float>(h, hp, nullptr);
+    } else {
+      rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, nullptr, (const double*)nullptr)
+                                : finish_setup<float>(h, rp, nullptr, (const float*)nullptr);
+    }
+  }
   if (rc) { g_create_error = h->err; cs_b200_destroy(h); return rc; }
   cudaEventRecord(h->ev1, h->stream);
   cudaEventSynchronize(h->ev1);
@@ -1519,6 +1803,58 @@ int cs_b200_get_csr(cs_b200_handle* h, int32_t* rowptr, int32_t* colidx, void* v
   if (rowptr) CK(h, cudaMemcpy(rowptr, h->d_rowptr, (size_t)(h->n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
   if (colidx) CK(h, cudaMemcpy(colidx, h->d_colidx, (size_t)h->nnz * sizeof(int), cudaMemcpyDeviceToHost));
   if (vals) CK(h, cudaMemcpy(vals, h->d_vals, (size_t)h->nnz * h->esize(), cudaMemcpyDeviceToHost));
+  return CS_B200_OK;
+}
+
+static const DevCsr* pick_level(cs_b200_handle* h, int level, int which, bool* is_f32, double* omega,
+                                int64_t* ncols) {
+  if (!h || level < 0 || which < 0 || which > 2) return nullptr;
+  std::vector<DevLevel>& lv = h->mixed ? h->lv32 : h->lv;
+  if (level >= (int)lv.size()) return nullptr;
+  if (which > 0 && level + 1 >= (int)lv.size()) return nullptr;
+  *is_f32 = h->mixed || h->dtype == CS_B200_F32;
+  *omega = lv[level].omega;
+  const DevCsr* m = which == 0 ? &lv[level].A : which == 1 ? &lv[level].P : &lv[level].R;
+  *ncols = which == 0 ? lv[level].n : which == 1 ? lv[level + 1].n : lv[level].n;
+  if (which == 2) *ncols = lv[level].n;
+  return m;
+}
+
+int cs_b200_level_info(cs_b200_handle* h, int level, int which, int64_t* nrows, int64_t* ncols,
+                       int64_t* nnz, double* omega, int* windowed) {
+  bool f32 = false;
+  double om = 0.0;
+  int64_t nc = 0;
+  const DevCsr* m = pick_level(h, level, which, &f32, &om, &nc);
+  if (!m) return CS_B200_ERR_ARG;
+  if (nrows) *nrows = m->nrows;
+  if (ncols) *ncols = nc;
+  if (nnz) *nnz = m->nnz;
+  if (omega) *omega = om;
+  if (windowed) *windowed = m->win_meta ? 1 : 0;
+  return CS_B200_OK;
+}
+
+int cs_b200_level_csr(cs_b200_handle* h, int level, int which, int32_t* rowptr, int32_t* colidx,
+                      double* vals) {
+  bool f32 = false;
+  double om = 0.0;
+  int64_t nc = 0;
+  const DevCsr* m = pick_level(h, level, which, &f32, &om, &nc);
+  if (!m) return CS_B200_ERR_ARG;
+  cudaSetDevice(h->device);
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (rowptr) CK(h, cudaMemcpy(rowptr, m->rowptr, (size_t)(m->nrows + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  if (colidx) CK(h, cudaMemcpy(colidx, m->colidx, (size_t)m->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+  if (vals) {
+    if (f32) {
+      std::vector<float> tmp((size_t)m->nnz);
+      CK(h, cudaMemcpy(tmp.data(), m->vals, (size_t)m->nnz * sizeof(float), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < m->nnz; ++i) vals[i] = (double)tmp[i];
+    } else {
+      CK(h, cudaMemcpy(vals, m->vals, (size_t)m->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+  }
   return CS_B200_OK;
 }
 

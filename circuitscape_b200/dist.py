@@ -60,14 +60,7 @@ def factor_from_device(n, nnz, rowptr, colidx, vals, solver, log_transform=False
     f.io_dtype = f.dtype
     f.solver = solver
     f._keep = (rowptr, colidx, vals)      # the handle borrows these buffers
-    opts = _lib.Opts()
-    opts.precond = _lib.PRECOND_AMG if solver.precond == "amg" else _lib.PRECOND_JACOBI
-    opts.panel_width = solver.panel_width
-    opts.check_every = solver.check_every
-    opts.use_graph = 2 if solver.use_graph == "chunk" else (1 if solver.use_graph else -1)
-    opts.log_transform = 1 if log_transform else 0
-    opts.window = {"auto": 0, "on": 1, "off": -1}[solver.window]
-    opts.mixed = 0 if solver.mixed else -1
+    opts = B200Factor._opts(solver, log_transform)
     torch.cuda.synchronize()   # the broadcast ran on torch's streams; the library uses its own
     rc = lib.cs_b200_create_from_device(n, nnz, C.c_void_p(rowptr.data_ptr()), C.c_void_p(colidx.data_ptr()),
                                         C.c_void_p(vals.data_ptr()), _lib.dtype_code(f.dtype),

@@ -42,6 +42,7 @@ class CUDASolver:
     window: str = "auto"             # TMA-staged windowed SpMM: auto | on | off
     f32_compute: bool = False        # precision = single: keep fp32 ON THE DEVICE too (see B200Factor)
     mixed: bool = True               # fp64 + AMG: fp32 V-cycle inside fp64 CG
+    setup: str = "auto"              # hierarchy / window records built: auto (device) | device | host
     superpose: bool = False          # pairwise driver: one solve per focal NODE, pairs by superposition
     batch_all_to_one: bool = False   # all-to-one: every iteration a column of ONE batch on one operator
     batch_one_to_all: bool = False   # one-to-all: one solve per iteration on ONE grounded operator
@@ -104,6 +105,7 @@ class B200Factor:
         opts.log_transform = 1 if log_transform else 0
         opts.window = {"auto": 0, "on": 1, "off": -1}[solver.window]
         opts.mixed = 0 if solver.mixed else -1
+        opts.setup = {"auto": 0, "host": 1, "device": 2}[solver.setup]
         return opts
 
     @classmethod
@@ -140,6 +142,35 @@ class B200Factor:
         va = np.empty(nnz.value, dtype=self.dtype)
         _lib.check(self._lib, self._h, self._lib.cs_b200_get_csr(self._h, _lib._ptr(rp), _lib._ptr(ci), _lib._ptr(va)))
         return sp.csr_matrix((va, ci, rp), shape=(n.value, n.value))
+
+    def levels(self):
+        """The multigrid hierarchy as SciPy matrices (downloaded; parity / debugging hook):
+        list of dicts with A, P, R (None on the coarsest level), omega, windowed flags."""
+        out = []
+        l = 0
+        while True:
+            lev = {}
+            for name, which in (("A", 0), ("P", 1), ("R", 2)):
+                nr, nc, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+                om, win = C.c_double(), C.c_int()
+                rc = self._lib.cs_b200_level_info(self._h, l, which, C.byref(nr), C.byref(nc), C.byref(nnz),
+                                                  C.byref(om), C.byref(win))
+                if rc != _lib.OK:
+                    lev[name] = None
+                    continue
+                rp = np.empty(nr.value + 1, dtype=np.int32)
+                ci = np.empty(nnz.value, dtype=np.int32)
+                va = np.empty(nnz.value, dtype=np.float64)
+                _lib.check(self._lib, self._h,
+                           self._lib.cs_b200_level_csr(self._h, l, which, _lib._ptr(rp), _lib._ptr(ci), _lib._ptr(va)))
+                lev[name] = sp.csr_matrix((va, ci, rp), shape=(nr.value, nc.value))
+                lev["omega"] = om.value
+                lev[name + "_windowed"] = bool(win.value)
+            if lev["A"] is None:
+                break
+            out.append(lev)
+            l += 1
+        return out
 
     # -- lifetime ---------------------------------------------------------
     def close(self):

@@ -74,7 +74,10 @@ typedef struct cs_b200_opts {
   int32_t mixed;          /* fp64 handles with AMG: run the V-cycle in fp32 (CG vectors,
                              dot products and the residual gate stay fp64): 0 auto (on),
                              -1 off                                                  */
-  int32_t reserved[5];
+  int32_t setup;          /* where the multigrid hierarchy and the windowed records are built:
+                             0 auto (on the device), 1 on the host (amg_host.hpp / win_host.hpp,
+                             the round-1 path, kept for A/B checks), 2 on the device           */
+  int32_t reserved[4];
 } cs_b200_opts;
 
 /* Per-call statistics (milliseconds measured with CUDA events on the solve stream). */
@@ -123,6 +126,16 @@ int cs_b200_create_from_raster(int64_t nrows, int64_t ncols, const void* g, int 
 /* Copy the handle's CSR (0-based, int32 indices, values of the handle's dtype) to host buffers
  * of n+1, nnz and nnz elements; any pointer may be NULL.  Parity / debugging hook.            */
 int cs_b200_get_csr(cs_b200_handle* h, int32_t* rowptr, int32_t* colidx, void* vals);
+
+/* Multigrid hierarchy inspection (parity / debugging hooks; levels exist only with the AMG
+ * preconditioner).  which: 0 = operator A_l, 1 = prolongator P_l (level l <- l+1), 2 = restriction
+ * R_l = P_l^T.  level_info returns CS_B200_ERR_ARG past the last level (and for P / R on the
+ * coarsest); omega = Jacobi damping of the level.  level_csr copies the operator as 0-based CSR
+ * with fp64 values (converted when the cycle runs in fp32); any pointer may be NULL.            */
+int cs_b200_level_info(cs_b200_handle* h, int level, int which, int64_t* nrows, int64_t* ncols,
+                       int64_t* nnz, double* omega, int* windowed);
+int cs_b200_level_csr(cs_b200_handle* h, int level, int which, int32_t* rowptr, int32_t* colidx,
+                      double* vals);
 
 /* n and nnz of the handle's operator. */
 int cs_b200_get_dims(const cs_b200_handle* h, int64_t* n, int64_t* nnz);

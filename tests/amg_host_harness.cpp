@@ -10,6 +10,11 @@ void* amgh_build(long n, long nnz, const int* ptr, const int* idx, const double*
   a.ptr.assign(ptr, ptr + n + 1); a.idx.assign(idx, idx + nnz); a.val.assign(val, val + nnz);
   return new Hierarchy(build_hierarchy(std::move(a)));
 }
+void* amgh_build2(long n, long nnz, const int* ptr, const int* idx, const double* val, int mis2) {
+  Csr a; a.nrows = a.ncols = n;
+  a.ptr.assign(ptr, ptr + n + 1); a.idx.assign(idx, idx + nnz); a.val.assign(val, val + nnz);
+  return new Hierarchy(build_hierarchy(std::move(a), 12, 200, mis2 != 0));
+}
 int amgh_nlevels(void* h) { return (int)((Hierarchy*)h)->levels.size(); }
 static const Csr& pick(void* h, int l, int which) {
   HostLevel& L = ((Hierarchy*)h)->levels[l];

@@ -54,11 +54,11 @@ def raster_pairwise_problem(golden, name, solver):
     return probs, flags, exp, None
 
 
-def run_raster_pairwise(golden, name, solver):
+def run_raster_pairwise(golden, name, solver, sink=None):
     """Returns an object with .resistances/.curmaps/.voltmaps/.cum_curmap/.max_curmap."""
     probs, flags, exp, pts = raster_pairwise_problem(golden, name, solver)
     if pts is None:
-        return cb.single_ground_all_pairs(probs[0][0], flags), exp
+        return cb.single_ground_all_pairs(probs[0][0], flags, sink=sink), exp
     n = len(pts)
     R = -np.ones((n, n))
     merged = None

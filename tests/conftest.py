@@ -1,3 +1,4 @@
+import ctypes
 import os
 import sys
 
@@ -10,6 +11,28 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def _cuda_device_present():
+    try:
+        cuda = ctypes.CDLL("libcuda.so.1")
+        if cuda.cuInit(0) != 0:
+            return False
+        n = ctypes.c_int(0)
+        return cuda.cuDeviceGetCount(ctypes.byref(n)) == 0 and n.value > 0
+    except OSError:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest` on a box without a GPU skips the gpu-marked tests instead of failing with
+    B200Unavailable (the product path itself still fails loudly: tests/test_abi.py)."""
+    if _cuda_device_present():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: gpu-marked parity tests need a B200 (pytest -m gpu on the GPU box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

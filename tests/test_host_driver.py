@@ -190,3 +190,76 @@ def test_raster_pairwise_driver_superposed(golden, i):
 def test_network_pairwise_driver_superposed(golden):
     prob, flags, exp = cases.network_pairwise_problem(golden, "sgNetworkVerify2", cb.CUDASolver(superpose=True))
     cases.check_network_pairwise(cb.single_ground_all_pairs(prob, flags), exp)
+
+
+# ---- round-2 advisor findings -----------------------------------------------------------------
+def test_network_log_transform_keeps_raw_cumulative_currents(golden):
+    """Only raster maps are log-transformed (src/out.jl:96); the network branch accumulates raw node
+    currents (src/out.jl:48-88), with or without `log_transform_maps`."""
+    prob, flags, exp = cases.network_pairwise_problem(golden, "sgNetworkVerify1", cb.CUDASolver())
+    plain = cb.single_ground_all_pairs(prob, flags)
+    prob2, flags2, _ = cases.network_pairwise_problem(golden, "sgNetworkVerify1", cb.CUDASolver())
+    flags2.outputflags.log_transform_maps = True
+    logged = cb.single_ground_all_pairs(prob2, flags2)
+    assert np.allclose(plain.cum_node, logged.cum_node, rtol=0, atol=1e-12)
+    cases.check_network_pairwise(logged, exp)
+
+
+def test_network_cumulative_branch_currents_and_row_order(golden):
+    """cum_branch follows `coords` (src/utils.jl:132-142) and matches the golden file; per-pair
+    branch rows come column-major like `_convert_to_3col` (src/out.jl:128-148)."""
+    prob, flags, exp = cases.network_pairwise_problem(golden, "sgNetworkVerify1", cb.CUDASolver())
+    r = cb.single_ground_all_pairs(prob, flags)
+    v = exp["branch_currents_cum.txt"].copy()
+    v[:, :2] += 1
+    mine = np.column_stack([prob.coords[0], prob.coords[1], r.cum_branch])
+    mine = mine[~np.isclose(mine[:, 2], 0.0, atol=1e-6)]
+    assert mine.shape == v.shape
+    assert np.sum((cases.sorted_rows(mine) - cases.sorted_rows(v)) ** 2) < 1e-6
+    gr, gc, _ = next(iter(r.branch.values()))
+    assert np.all(gr < gc)
+    key = gc.astype(np.int64) * (gc.max() + 1) + gr
+    assert np.all(np.diff(key) > 0)
+
+
+def test_unknown_branch_raises():
+    from circuitscape_b200.core import _BranchIndex
+    idx = _BranchIndex((np.array([1, 2]), np.array([2, 3])))
+    cum = np.zeros(2)
+    idx.add(cum, (np.array([2, 3]), np.array([1, 2]), np.array([0.5, 0.25])))      # reversed edges are found
+    assert np.allclose(cum, [0.5, 0.25])
+    with pytest.raises(KeyError):
+        idx.add(cum, (np.array([1]), np.array([3]), np.array([1.0])))
+
+
+class _Sink:
+    def __init__(self):
+        self.volt, self.cur, self.net = {}, {}, {}
+
+    def voltmap(self, key, grid):
+        self.volt[key] = grid.copy()
+
+    def curmap(self, key, grid):
+        self.cur[key] = grid.copy()
+
+    def network(self, key, comp, v, cur, branch):
+        self.net[key] = (comp, v, cur, branch)
+
+
+def test_sink_streams_maps_instead_of_keeping_them(golden):
+    """With a sink the per-pair maps are handed over as each batch finishes and not retained
+    (the reference writes and drops them inside postprocess, src/core.jl:655-683)."""
+    kept, exp = cases.run_raster_pairwise(golden, "sgVerify1", cb.CUDASolver())
+    sink = _Sink()
+    streamed, _ = cases.run_raster_pairwise(golden, "sgVerify1", cb.CUDASolver(), sink=sink)
+    assert not streamed.curmaps and not streamed.voltmaps
+    assert sink.cur.keys() == kept.curmaps.keys() and sink.volt.keys() == kept.voltmaps.keys()
+    for k in kept.curmaps:
+        assert np.array_equal(sink.cur[k], kept.curmaps[k])
+    for k in kept.voltmaps:
+        assert np.array_equal(sink.volt[k], kept.voltmaps[k])
+    assert np.array_equal(streamed.cum_curmap, kept.cum_curmap)
+    prob, flags, _ = cases.network_pairwise_problem(golden, "sgNetworkVerify2", cb.CUDASolver())
+    nsink = _Sink()
+    r = cb.single_ground_all_pairs(prob, flags, sink=nsink)
+    assert not r.curmaps and not r.branch and nsink.net
