@@ -330,16 +330,30 @@ def main():
     if rank == 0:
         L, src, dst = workload(args, npairs)
     t_asm = time.time() - t_asm
-    # ---- replicate the operator: one NCCL broadcast of the CSR -------
+    # ---- replicate the operator: one NCCL broadcast of the CSR, behind the C ABI:
+    # torch.distributed only carries the 128-byte NCCL id and three integers between the ranks
     t0 = time.time()
+    comm = None
     if distributed:
-        n, nnz, rp, ci, va = cdist.broadcast_csr(L, dist, dev)
+        def exchange(raw):
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if raw is not None:
+                t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, src=0)
+            return bytes(t.cpu().tolist())
+        comm = cdist.Comm(local, rank, world, exchange)
+        meta = torch.zeros(3, dtype=torch.int64, device=dev)
+        if rank == 0:
+            meta = torch.tensor([L.shape[0], L.nnz, npairs], dtype=torch.int64, device=dev)
+        dist.broadcast(meta, src=0)
+        n, nnz = int(meta[0]), int(meta[1])
         pairs = torch.zeros((2, npairs), dtype=torch.int64, device=dev)
         if rank == 0:
             pairs = torch.as_tensor(np.stack([src, dst]), device=dev)
         dist.broadcast(pairs, src=0)
         src, dst = pairs[0].cpu().numpy(), pairs[1].cpu().numpy()
-        factor = cdist.factor_from_device(n, nnz, rp, ci, va, solver)
+        t0 = time.time()
+        factor = comm.create_factor(L if rank == 0 else None, solver, shape=(n, nnz))
     else:
         n, nnz = L.shape[0], L.nnz
         factor = cb.construct_cholesky_factor(L, solver)
@@ -352,16 +366,16 @@ def main():
     def step():
         factor.reset_currents()
         out = factor.solve_pairs(msrc, mdst, accumulate=True)
-        if distributed:
-            R = cdist.gather_pairs(mine, out["R"], npairs, dist, device=dev)
-            cdist.reduce_currents(factor, dist)
+        if distributed:                                   # end of the job: one gather, one reduction
+            R = comm.gather_pairs(mine, out["R"], npairs)
+            comm.reduce_currents(factor)
         else:
             R = out["R"]
         return R, out, factor.stats()
 
     def timed(fn, steps):
         if distributed:
-            dist.barrier()
+            comm.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
@@ -369,14 +383,11 @@ def main():
         res = [fn() for _ in range(steps)]
         e1.record(ext)
         torch.cuda.synchronize()
-        if distributed:
-            dist.barrier()
         wall = time.time() - t0
         ms = e0.elapsed_time(e1)
-        if distributed:
-            t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, wall = float(t[0]), float(t[1]) / 1e3
+        if distributed:                                   # device time: max over ranks
+            ms, wallms = comm.max([ms, wall * 1e3])
+            wall = wallms / 1e3
         return ms, wall, res
 
     # clocks are sampled from the first warm-up step to the end of the timed region (the
@@ -428,7 +439,7 @@ def main():
                 s_ = factor.stats()
                 h2d += int(s_["h2d_bytes"]); d2h += int(s_["d2h_bytes"])
             if distributed:
-                r = cdist.gather_pairs(mine, r, npairs, dist, device=dev)
+                r = comm.gather_pairs(mine, r, npairs)
             return r
 
         rhs[:] = 0.0
@@ -560,6 +571,9 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if distributed:
+        factor.close()
+        comm.barrier()
+        comm.close()
         dist.barrier()
         dist.destroy_process_group()
 

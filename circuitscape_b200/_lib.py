@@ -86,6 +86,16 @@ _PROTOS = {
     "cs_b200_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "cs_b200_profile_spmm": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "cs_b200_profile_bytes": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "cs_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "cs_b200_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(_H)]),
+    "cs_b200_comm_destroy": (None, [_H]),
+    "cs_b200_comm_last_error": (C.c_char_p, [_H]),
+    "cs_b200_create_bcast": (C.c_int, [_H, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_int, C.c_int, C.POINTER(Opts), C.POINTER(_H)]),
+    "cs_b200_comm_reduce_currents": (C.c_int, [_H, _H]),
+    "cs_b200_comm_gather_pairs": (C.c_int, [_H, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cs_b200_comm_max_double": (C.c_int, [_H, C.c_void_p, C.c_int]),
+    "cs_b200_comm_barrier": (C.c_int, [_H]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 

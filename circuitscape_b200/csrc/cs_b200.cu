@@ -559,7 +559,8 @@ int adopt_levels(cs_b200_handle* h, csb_dev::DHierarchy& hier, std::vector<DevLe
 }
 
 template <typename T>
-int setup_amg_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job) {
+int setup_amg_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job,
+                     const csb_dev::DeviceSeed* dseed) {
   const bool verbose = std::getenv("CS_B200_VERBOSE") != nullptr;
   csb_dev::DCsr a0;
   a0.nrows = a0.ncols = h->n;
@@ -580,7 +581,7 @@ int setup_amg_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev:
   }
   Tick tick;
   csb_dev::DHierarchy hier;
-  int rc = csb_dev::build_hierarchy(h->stream, a0, hp, job, 12, 200, hier, h->err, verbose);
+  int rc = csb_dev::build_hierarchy(h->stream, a0, hp, job, dseed, 12, 200, hier, h->err, verbose);
   auto done = [&](int code) {
     cudaStreamSynchronize(h->stream);
     csb_dev::free_hierarchy(hier);
@@ -626,7 +627,8 @@ int setup_amg_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev:
 }
 
 template <typename T>
-int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job) {
+int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job,
+                        const csb_dev::DeviceSeed* dseed = nullptr) {
   h->A0 = DevCsr{h->d_rowptr, h->d_colidx, h->d_vals, nullptr, 0, (int)h->n, h->nnz, 1};
   int rc = device_row_blocks(h, h->A0, NT);
   if (rc) { csb_dev::seed_discard(job); return rc; }
@@ -643,7 +645,7 @@ int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_d
     tick("finest operator: windows");
   }
   if (want_amg) {
-    rc = setup_amg_device<T>(h, hp, job);
+    rc = setup_amg_device<T>(h, hp, job, dseed);
     if (rc) return rc;
   } else {
     csb_dev::seed_discard(job);
@@ -2194,6 +2196,313 @@ int cs_b200_solve_pairs_superposed(cs_b200_handle* h, int64_t np, const int64_t*
                                                  (float*)volt, (float*)curr, accumulate, point_iters, relres);
   end_call(h);
   return rc;
+}
+
+}  // extern "C"
+// ---------------------------------------------------------------------------------------------
+// multi-GPU: NCCL behind the C ABI (loaded at run time, so a single-GPU user needs no NCCL)
+// ---------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+
+namespace {
+
+struct NcclId { char internal[128]; };
+typedef void* ncclComm_p;
+// enums of nccl.h (stable across NCCL 2.x)
+enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_INT64 = 4, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };
+enum { NCCL_SUM = 0, NCCL_MAX = 2 };
+
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(ncclComm_p*, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_p) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_p, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string err;
+};
+
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.lib || !api.err.empty()) return api;
+  const char* names[] = {std::getenv("CS_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm) continue;
+    api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) { api.err = std::string("cannot load NCCL (libnccl.so.2): ") + dlerror(); return api; }
+  auto sym = [&](const char* s) { void* p = dlsym(api.lib, s); if (!p) api.err = std::string("NCCL symbol missing: ") + s; return p; };
+  api.GetUniqueId = (int (*)(NcclId*))sym("ncclGetUniqueId");
+  api.CommInitRank = (int (*)(ncclComm_p*, int, NcclId, int))sym("ncclCommInitRank");
+  api.CommDestroy = (int (*)(ncclComm_p))sym("ncclCommDestroy");
+  api.Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_p, cudaStream_t))sym("ncclBroadcast");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_p, cudaStream_t))sym("ncclAllReduce");
+  api.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_p, cudaStream_t))sym("ncclAllGather");
+  api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+  return api;
+}
+
+thread_local std::string g_comm_error;
+
+}  // namespace
+
+struct cs_b200_comm {
+  int device = 0, rank = 0, nranks = 1;
+  ncclComm_p comm = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+};
+
+namespace {
+int comm_err(cs_b200_comm* c, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_comm_error = buf;
+  return code;
+}
+#define CKN(c, call)                                                                                  \
+  do {                                                                                                \
+    int _r = (call);                                                                                  \
+    if (_r != 0) return comm_err(c, CS_B200_ERR_CUDA, "NCCL error %s (%s)", nccl_api().GetErrorString(_r), #call); \
+  } while (0)
+#define CKU(c, call)                                                                                  \
+  do {                                                                                                \
+    cudaError_t _e = (call);                                                                          \
+    if (_e != cudaSuccess) return comm_err(c, CS_B200_ERR_CUDA, "CUDA error %s (%s)", cudaGetErrorString(_e), #call); \
+  } while (0)
+}  // namespace
+
+extern "C" {
+
+int cs_b200_comm_unique_id(void* id128) {
+  if (!id128) return comm_err(nullptr, CS_B200_ERR_ARG, "id128 is NULL");
+  NcclApi& api = nccl_api();
+  if (!api.err.empty()) return comm_err(nullptr, CS_B200_ERR_UNSUPPORTED, "%s", api.err.c_str());
+  NcclId id;
+  CKN(nullptr, api.GetUniqueId(&id));
+  std::memcpy(id128, &id, sizeof id);
+  return CS_B200_OK;
+}
+
+int cs_b200_comm_init(int device, int rank, int nranks, const void* id128, cs_b200_comm** out) {
+  if (!out || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return comm_err(nullptr, CS_B200_ERR_ARG, "bad comm_init arguments");
+  *out = nullptr;
+  NcclApi& api = nccl_api();
+  if (!api.err.empty()) return comm_err(nullptr, CS_B200_ERR_UNSUPPORTED, "%s", api.err.c_str());
+  CKU(nullptr, cudaSetDevice(device));
+  cs_b200_comm* c = new cs_b200_comm();
+  c->device = device; c->rank = rank; c->nranks = nranks;
+  NcclId id;
+  std::memcpy(&id, id128, sizeof id);
+  int r = api.CommInitRank(&c->comm, nranks, id, rank);
+  if (r != 0) { comm_err(nullptr, CS_B200_ERR_CUDA, "NCCL error %s (ncclCommInitRank)", api.GetErrorString(r)); delete c; return CS_B200_ERR_CUDA; }
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { comm_err(nullptr, CS_B200_ERR_CUDA, "CUDA error %s creating the comm stream", cudaGetErrorString(e)); api.CommDestroy(c->comm); delete c; return CS_B200_ERR_CUDA; }
+  *out = c;
+  return CS_B200_OK;
+}
+
+void cs_b200_comm_destroy(cs_b200_comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->comm) nccl_api().CommDestroy(c->comm);
+  delete c;
+}
+
+const char* cs_b200_comm_last_error(const cs_b200_comm* c) { return c ? c->err.c_str() : g_comm_error.c_str(); }
+
+int cs_b200_comm_barrier(cs_b200_comm* c) {
+  if (!c) return CS_B200_ERR_ARG;
+  cudaSetDevice(c->device);
+  int* d = nullptr;
+  CKU(c, cudaMalloc(&d, sizeof(int)));
+  cudaMemsetAsync(d, 0, sizeof(int), c->stream);
+  int r = nccl_api().AllReduce(d, d, 1, NCCL_INT32, NCCL_SUM, c->comm, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (r != 0) return comm_err(c, CS_B200_ERR_CUDA, "NCCL error %s (barrier)", nccl_api().GetErrorString(r));
+  CKU(c, e);
+  return CS_B200_OK;
+}
+
+int cs_b200_comm_max_double(cs_b200_comm* c, double* v, int count) {
+  if (!c || !v || count < 1) return CS_B200_ERR_ARG;
+  cudaSetDevice(c->device);
+  double* d = nullptr;
+  CKU(c, cudaMalloc(&d, (size_t)count * sizeof(double)));
+  cudaMemcpyAsync(d, v, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  int r = nccl_api().AllReduce(d, d, (size_t)count, NCCL_FLOAT64, NCCL_MAX, c->comm, c->stream);
+  cudaMemcpyAsync(v, d, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (r != 0) return comm_err(c, CS_B200_ERR_CUDA, "NCCL error %s (max_double)", nccl_api().GetErrorString(r));
+  CKU(c, e);
+  return CS_B200_OK;
+}
+
+int cs_b200_comm_reduce_currents(cs_b200_comm* c, cs_b200_handle* h) {
+  if (!c || !h || h->device != c->device) return comm_err(c, CS_B200_ERR_ARG, "bad reduce_currents arguments");
+  cudaSetDevice(c->device);
+  const int dt = h->dtype == CS_B200_F64 ? NCCL_FLOAT64 : NCCL_FLOAT32;
+  // on the handle's own stream: ordered right behind the last accumulation kernel, no host sync between
+  CKN(c, nccl_api().AllReduce(h->d_cum, h->d_cum, (size_t)h->n, dt, NCCL_SUM, c->comm, h->stream));
+  CKN(c, nccl_api().AllReduce(h->d_max, h->d_max, (size_t)h->n, dt, NCCL_MAX, c->comm, h->stream));
+  CKU(c, cudaStreamSynchronize(h->stream));
+  return CS_B200_OK;
+}
+
+int cs_b200_comm_gather_pairs(cs_b200_comm* c, int64_t k_total, const int64_t* my_idx, int64_t k_mine,
+                              const double* my_R, double* R_all) {
+  if (!c || k_total < 1 || k_mine < 0 || (k_mine > 0 && (!my_idx || !my_R)) || !R_all)
+    return comm_err(c, CS_B200_ERR_ARG, "bad gather_pairs arguments");
+  cudaSetDevice(c->device);
+  // fixed-size slots: ceil(k_total / nranks) (index, value) pairs per rank, index -1 = empty
+  const int64_t slot = (k_total + c->nranks - 1) / c->nranks;
+  if (k_mine > slot) return comm_err(c, CS_B200_ERR_ARG, "rank %d holds %lld pairs, more than ceil(k_total / nranks) = %lld", c->rank, (long long)k_mine, (long long)slot);
+  std::vector<double> send((size_t)2 * slot, -1.0), recv((size_t)2 * slot * c->nranks);
+  for (int64_t i = 0; i < k_mine; ++i) { send[2 * i] = (double)my_idx[i]; send[2 * i + 1] = my_R[i]; }
+  double *ds = nullptr, *dr = nullptr;
+  CKU(c, cudaMalloc(&ds, send.size() * sizeof(double)));
+  cudaError_t e = cudaMalloc(&dr, recv.size() * sizeof(double));
+  if (e != cudaSuccess) { cudaFree(ds); CKU(c, e); }
+  cudaMemcpyAsync(ds, send.data(), send.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  int r = nccl_api().AllGather(ds, dr, send.size(), NCCL_FLOAT64, c->comm, c->stream);
+  cudaMemcpyAsync(recv.data(), dr, recv.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  e = cudaStreamSynchronize(c->stream);
+  cudaFree(ds); cudaFree(dr);
+  if (r != 0) return comm_err(c, CS_B200_ERR_CUDA, "NCCL error %s (gather_pairs)", nccl_api().GetErrorString(r));
+  CKU(c, e);
+  for (int64_t i = 0; i < k_total; ++i) R_all[i] = -1.0;
+  for (size_t q = 0; q + 1 < recv.size(); q += 2) {
+    const int64_t idx = (int64_t)recv[q];
+    if (idx >= 0 && idx < k_total) R_all[idx] = recv[q + 1];
+  }
+  return CS_B200_OK;
+}
+
+int cs_b200_create_bcast(cs_b200_comm* c, int root, int64_t n, int64_t nnz, const void* rowptr,
+                         const void* colidx, const void* vals, int index_bits, int index_base,
+                         int dtype, const cs_b200_opts* opts, cs_b200_handle** out) {
+  if (!out) return comm_err(c, CS_B200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (!c || root < 0 || root >= c->nranks || n <= 0 || nnz <= 0 || (dtype != CS_B200_F32 && dtype != CS_B200_F64) ||
+      nnz >= (int64_t)1 << 31 || n >= (int64_t)1 << 31 || (index_bits != 32 && index_bits != 64) ||
+      (index_base != 0 && index_base != 1))
+    return comm_err(c, CS_B200_ERR_ARG, "bad create_bcast arguments");
+  const bool is_root = c->rank == root;
+  if (is_root && (!rowptr || !colidx || !vals)) return comm_err(c, CS_B200_ERR_ARG, "the root rank must pass the matrix");
+  cs_b200_handle* h = new cs_b200_handle();
+  h->n = n; h->nnz = nnz; h->dtype = dtype; h->device = c->device;
+  int rc = common_create(h, opts);
+  auto fail = [&](int code) { c->err = h->err; g_create_error = h->err; cs_b200_destroy(h); return code; };
+  if (rc) return fail(rc);
+  cudaEventRecord(h->ev0, h->stream);
+  const size_t es = h->esize();
+  const bool amg = h->opts.precond == CS_B200_PRECOND_AMG && n > 200 && h->opts.setup != 1;
+  csb_dev::SeedJob* job = nullptr;
+  const csb_dev::HostPattern hp{rowptr, colidx, index_bits, index_base};
+  if (is_root && amg) job = csb_dev::seed_start(n, hp);   // overlaps the upload and the broadcast
+  auto fail_job = [&](int code) { csb_dev::seed_discard(job); job = nullptr; return fail(code); };
+#define CKB(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (%s)", cudaGetErrorString(_e), #call);           \
+      return fail_job(CS_B200_ERR_CUDA);                                                           \
+    }                                                                                              \
+  } while (0)
+#define CKBN(call)                                                                                 \
+  do {                                                                                             \
+    int _r = (call);                                                                               \
+    if (_r != 0) {                                                                                 \
+      set_err(h, CS_B200_ERR_CUDA, "NCCL error %s (%s)", nccl_api().GetErrorString(_r), #call);    \
+      return fail_job(CS_B200_ERR_CUDA);                                                           \
+    }                                                                                              \
+  } while (0)
+  CKB(cudaMalloc(&h->d_rowptr, (size_t)(n + 1) * sizeof(int)));
+  CKB(cudaMalloc(&h->d_colidx, (size_t)nnz * sizeof(int)));
+  CKB(cudaMalloc(&h->d_vals, (size_t)nnz * es));
+  if (is_root) {
+    if (index_bits == 32 && index_base == 0) {
+      CKB(cudaMemcpyAsync(h->d_rowptr, rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      CKB(cudaMemcpyAsync(h->d_colidx, colidx, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    } else {
+      const size_t ib = index_bits / 8;
+      void* raw = nullptr;
+      CKB(cudaMalloc(&raw, std::max<size_t>((size_t)(n + 1), (size_t)nnz) * ib));
+      cudaError_t e = cudaMemcpyAsync(raw, rowptr, (size_t)(n + 1) * ib, cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) e = (cudaError_t)csb_dev::narrow_indices(h->stream, raw, index_bits, index_base, n + 1, h->d_rowptr);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(raw, colidx, (size_t)nnz * ib, cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) e = (cudaError_t)csb_dev::narrow_indices(h->stream, raw, index_bits, index_base, nnz, h->d_colidx);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      cudaFree(raw);
+      CKB(e);
+    }
+    CKB(cudaMemcpyAsync(h->d_vals, vals, (size_t)nnz * es, cudaMemcpyHostToDevice, h->stream));
+  }
+  // one broadcast of the CSR, on the handle's stream behind the upload
+  NcclApi& api = nccl_api();
+  CKBN(api.Broadcast(h->d_rowptr, h->d_rowptr, (size_t)(n + 1), NCCL_INT32, root, c->comm, h->stream));
+  CKBN(api.Broadcast(h->d_colidx, h->d_colidx, (size_t)nnz, NCCL_INT32, root, c->comm, h->stream));
+  CKBN(api.Broadcast(h->d_vals, h->d_vals, (size_t)nnz * es, NCCL_INT8, root, c->comm, h->stream));
+  // the root's ordered aggregation seeds travel the same way (n ints) instead of every rank
+  // downloading the pattern and repeating the pass
+  int* d_seed = nullptr;
+  csb_dev::DeviceSeed ds;
+  if (amg) {
+    CKB(cudaMalloc(&d_seed, (size_t)(n + 1) * sizeof(int)));
+    if (is_root) {
+      const int* seed = nullptr;
+      int64_t cnt = 0;
+      const int nagg = csb_dev::seed_wait(job, &seed, &cnt);
+      cudaError_t e = cudaMemcpyAsync(d_seed, seed, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_seed + n, &nagg, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      csb_dev::seed_discard(job);
+      job = nullptr;
+      if (e != cudaSuccess) { cudaFree(d_seed); CKB(e); }
+    }
+    int r = api.Broadcast(d_seed, d_seed, (size_t)(n + 1), NCCL_INT32, root, c->comm, h->stream);
+    int nagg = 0;
+    cudaError_t e = cudaMemcpyAsync(&nagg, d_seed + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (r != 0 || e != cudaSuccess) {
+      cudaFree(d_seed);
+      set_err(h, CS_B200_ERR_CUDA, "broadcast of the aggregation seeds failed (%s)", r != 0 ? api.GetErrorString(r) : cudaGetErrorString(e));
+      return fail_job(CS_B200_ERR_CUDA);
+    }
+    ds.d_seed = d_seed;
+    ds.nagg = nagg;
+  }
+#undef CKB
+#undef CKBN
+  if (h->opts.setup != 1) {
+    const csb_dev::HostPattern none{};
+    rc = dtype == CS_B200_F64 ? finish_setup_device<double>(h, none, nullptr, amg ? &ds : nullptr)
+                              : finish_setup_device<float>(h, none, nullptr, amg ? &ds : nullptr);
+  } else {
+    std::vector<int> rp(n + 1);
+    cudaError_t e = cudaMemcpy(rp.data(), h->d_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { cudaFree(d_seed); set_err(h, CS_B200_ERR_CUDA, "CUDA error %s reading rowptr", cudaGetErrorString(e)); return fail(CS_B200_ERR_CUDA); }
+    rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, nullptr, (const double*)nullptr)
+                              : finish_setup<float>(h, rp, nullptr, (const float*)nullptr);
+  }
+  cudaFree(d_seed);
+  if (rc) return fail(rc);
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.setup_ms = ms;
+  *out = h;
+  return CS_B200_OK;
 }
 
 }  // extern "C"

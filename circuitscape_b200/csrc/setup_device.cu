@@ -533,6 +533,13 @@ SeedJob* seed_start(int64_t n, const HostPattern& hp) {
   return job;
 }
 
+int seed_wait(SeedJob* job, const int** seed, int64_t* count) {
+  const int nagg = job->fut.get();
+  *seed = job->seed.data();
+  *count = (int64_t)job->seed.size();
+  return nagg;
+}
+
 void seed_discard(SeedJob* job) {
   if (!job) return;
   if (job->fut.valid()) job->fut.wait();
@@ -584,8 +591,8 @@ int convert_values(cudaStream_t s, const float* d_in, double* d_out, int64_t cou
 // ---------------------------------------------------------------------------------------------
 // hierarchy
 // ---------------------------------------------------------------------------------------------
-int build_hierarchy(cudaStream_t s, const DCsr& A0, const HostPattern& hp0, SeedJob* pre, int max_levels,
-                    int max_coarse, DHierarchy& out, std::string& err, bool verbose) {
+int build_hierarchy(cudaStream_t s, const DCsr& A0, const HostPattern& hp0, SeedJob* pre, const DeviceSeed* dseed,
+                    int max_levels, int max_coarse, DHierarchy& out, std::string& err, bool verbose) {
   struct JobGuard { SeedJob*& j; ~JobGuard() { seed_discard(j); j = nullptr; } } job_guard{pre};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -601,7 +608,7 @@ int build_hierarchy(cudaStream_t s, const DCsr& A0, const HostPattern& hp0, Seed
   // and the power iteration; without a host copy of the pattern it is downloaded first
   std::vector<int> h_ptr, h_idx;
   HostPattern hp = hp0;
-  if (!pre && A0.nrows > max_coarse && max_levels > 1 && (!hp.rowptr || !hp.colidx)) {
+  if (!pre && !dseed && A0.nrows > max_coarse && max_levels > 1 && (!hp.rowptr || !hp.colidx)) {
     h_ptr.resize((size_t)A0.nrows + 1);
     h_idx.resize((size_t)std::max<int64_t>(A0.nnz, 1));
     CKD(cudaMemcpyAsync(h_ptr.data(), A0.ptr, (size_t)(A0.nrows + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -620,8 +627,9 @@ int build_hierarchy(cudaStream_t s, const DCsr& A0, const HostPattern& hp0, Seed
     std::vector<int> seed;
     std::future<int> fut;
     const auto t_agg = std::chrono::steady_clock::now();
-    const bool use_pre = coarsen && l == 0 && pre != nullptr;
-    if (coarsen && !use_pre) {
+    const bool use_dev = coarsen && l == 0 && dseed != nullptr;
+    const bool use_pre = coarsen && l == 0 && pre != nullptr && !use_dev;
+    if (coarsen && !use_pre && !use_dev) {
       const HostPattern hpl = hp;
       fut = std::async(std::launch::async, [n, hpl, &seed]() { return greedy_seed_any(n, hpl, seed); });
     }
@@ -633,7 +641,9 @@ int build_hierarchy(cudaStream_t s, const DCsr& A0, const HostPattern& hp0, Seed
     tick("diag + lambda_max", l);
     if (!coarsen) break;
     int nagg;
-    if (use_pre) {
+    if (use_dev) {
+      nagg = dseed->nagg;
+    } else if (use_pre) {
       nagg = pre->fut.get();
       seed.swap(pre->seed);
     } else {
@@ -648,9 +658,10 @@ int build_hierarchy(cudaStream_t s, const DCsr& A0, const HostPattern& hp0, Seed
     CKD(d_seed.alloc((size_t)n, s));
     CKD(d_agg.alloc((size_t)n, s));
     CKD(d_cnt.alloc((size_t)nagg, s));
-    CKD(cudaMemcpyAsync(d_seed.p, seed.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (!use_dev) CKD(cudaMemcpyAsync(d_seed.p, seed.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
     k_zero_int<<<grid_for(nagg), TPB, 0, s>>>(d_cnt.p, nagg);
-    k_agg_join<<<grid_for(n), TPB, 0, s>>>((int)n, lv.A.ptr, lv.A.idx, lv.A.val, d_seed.p, d_agg.p, d_cnt.p);
+    k_agg_join<<<grid_for(n), TPB, 0, s>>>((int)n, lv.A.ptr, lv.A.idx, lv.A.val, use_dev ? dseed->d_seed : d_seed.p,
+                                            d_agg.p, d_cnt.p);
     CKD(cudaGetLastError());
     CKD(cudaStreamSynchronize(s));   // `seed` (pageable) must outlive the copy
     d_seed.release();

@@ -64,11 +64,20 @@ struct SeedJob;
 SeedJob* seed_start(int64_t n, const HostPattern& hp);
 void seed_discard(SeedJob* job);   // waits for the thread and frees the job (error paths)
 
+int seed_wait(SeedJob* job, const int** seed, int64_t* count);   // joins; *seed stays valid until seed_discard
+
+// level-0 seeds already on the device (multi-GPU: the root's seed pass, broadcast over NCCL)
+struct DeviceSeed {
+  const int* d_seed = nullptr;     // n entries, -1 = free
+  int nagg = 0;
+};
+
 // Build the hierarchy of A0 (device, fp64 values; borrowed, not freed).  `pre`: a job started with
-// seed_start on the same pattern (consumed), or null.  Returns 0 or a cudaError_t
+// seed_start on the same pattern (consumed), or null; `dseed`: level-0 seeds resident on the device
+// (takes precedence), or null.  Returns 0 or a cudaError_t
 // (as int) / -1 with `err` set.
-int build_hierarchy(cudaStream_t stream, const DCsr& A0, const HostPattern& hp, SeedJob* pre, int max_levels,
-                    int max_coarse, DHierarchy& out, std::string& err, bool verbose);
+int build_hierarchy(cudaStream_t stream, const DCsr& A0, const HostPattern& hp, SeedJob* pre, const DeviceSeed* dseed,
+                    int max_levels, int max_coarse, DHierarchy& out, std::string& err, bool verbose);
 
 // Greedy row blocks (<= max_rows rows and <= nnz_cap entries; a longer row stands alone) -- the
 // partition win_host.hpp::row_blocks / build_row_blocks compute sequentially.  *d_bstart: device,

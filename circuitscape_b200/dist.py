@@ -69,6 +69,93 @@ def factor_from_device(n, nnz, rowptr, colidx, vals, solver, log_transform=False
     return f
 
 
+class Comm:
+    """NCCL communicator behind the C ABI (cs_b200_comm_*): what a Julia host would use.  The only
+    thing the host language moves is the 128-byte unique id from rank 0 to the other ranks --
+    `exchange(id_bytes_or_None) -> id_bytes` (torch.distributed broadcast, MPI, a file ...)."""
+
+    def __init__(self, device, rank, nranks, exchange):
+        from . import _lib
+        self._lib = lib = _lib.load()
+        self.rank, self.nranks, self.device = rank, nranks, device
+        ident = (C.c_char * 128)()
+        if rank == 0:
+            _lib.check(lib, None, lib.cs_b200_comm_unique_id(C.cast(ident, C.c_void_p)))
+        raw = exchange(bytes(ident.raw) if rank == 0 else None)
+        buf = (C.c_char * 128).from_buffer_copy(raw)
+        self._c = C.c_void_p()
+        rc = lib.cs_b200_comm_init(device, rank, nranks, C.cast(buf, C.c_void_p), C.byref(self._c))
+        self._check(rc, None)
+
+    def _check(self, rc, c):
+        if rc != 0:
+            from . import _lib
+            msg = self._lib.cs_b200_comm_last_error(c)
+            raise _lib.B200Error(rc, msg.decode() if msg else f"libcsb200 comm error {rc}")
+
+    def close(self):
+        if getattr(self, "_c", None) is not None and self._c.value:
+            self._lib.cs_b200_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+    __del__ = close
+
+    def create_factor(self, matrix, solver, root=0, shape=None, log_transform=False):
+        """cs_b200_create_bcast: `matrix` (scipy CSR) on the root, None elsewhere; `shape` =
+        (n, nnz, is_f64) must be known on every rank (the host broadcasts three integers)."""
+        from . import _lib
+        from .solver import B200Factor
+        import scipy.sparse as sp
+        f = B200Factor.__new__(B200Factor)
+        f._lib = self._lib
+        f._h = C.c_void_p()
+        f.solver = solver
+        f.io_dtype = np.dtype(solver.dtype)
+        f.dtype = np.dtype(solver.device_dtype)
+        opts = B200Factor._opts(solver, log_transform)
+        if matrix is not None:
+            m = sp.csr_matrix(matrix)
+            m.sort_indices()
+            n, nnz = m.shape[0], m.nnz
+            vals = np.ascontiguousarray(m.data, dtype=f.dtype)
+            rp = np.ascontiguousarray(m.indptr)
+            ci = np.ascontiguousarray(m.indices)
+            if ci.dtype != rp.dtype:
+                ci = ci.astype(rp.dtype)
+            bits = 64 if rp.dtype == np.int64 else 32
+            args = (_lib._ptr(rp), _lib._ptr(ci), _lib._ptr(vals))
+        else:
+            n, nnz = int(shape[0]), int(shape[1])
+            bits = 32
+            args = (None, None, None)
+        f.n = n
+        rc = self._lib.cs_b200_create_bcast(self._c, root, n, nnz, *args, bits, 0, _lib.dtype_code(f.dtype),
+                                            C.byref(opts), C.byref(f._h))
+        self._check(rc, self._c)
+        return f
+
+    def reduce_currents(self, factor):
+        self._check(self._lib.cs_b200_comm_reduce_currents(self._c, factor._h), self._c)
+
+    def gather_pairs(self, local_idx, local_vals, npairs):
+        from . import _lib
+        idx = np.ascontiguousarray(local_idx, dtype=np.int64)
+        val = np.ascontiguousarray(local_vals, dtype=np.float64)
+        out = np.empty(npairs, dtype=np.float64)
+        rc = self._lib.cs_b200_comm_gather_pairs(self._c, npairs, _lib._ptr(idx), len(idx), _lib._ptr(val), _lib._ptr(out))
+        self._check(rc, self._c)
+        return out
+
+    def max(self, values):
+        from . import _lib
+        v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        self._check(self._lib.cs_b200_comm_max_double(self._c, _lib._ptr(v), len(v)), self._c)
+        return v
+
+    def barrier(self):
+        self._check(self._lib.cs_b200_comm_barrier(self._c), self._c)
+
+
 def gather_pairs(local_idx, local_vals, npairs, dist, device="cpu"):
     """all_gather variable-length (index, value) shards into a dense length-npairs
     vector on every rank."""

@@ -236,6 +236,45 @@ int cs_b200_profile_spmm(cs_b200_handle* h, int enable, double* total_ms, int64_
  * the launches timed since profiling was last enabled; read BEFORE disabling.          */
 int cs_b200_profile_bytes(cs_b200_handle* h, double* algorithmic_bytes);
 
+/* ---- multi-GPU: pair sharding behind the C ABI -----------------------------
+ * One process (or thread) per GPU.  The path shards over independent focal pairs against ONE
+ * replicated read-only operator -- the axis the reference threads over (src/core.jl:262-272) --
+ * so the only collectives are: the broadcast of the matrix from the root, and at the END of a job
+ * the gather of the per-pair resistances and the SUM / MAX reduction of the cumulative / max
+ * current vectors (src/out.jl:100-107).  NCCL is loaded at run time (dlopen "libnccl.so.2"); the
+ * host language only has to move the 128-byte unique id from rank 0 to the other ranks (MPI
+ * broadcast, a socket, a file) -- nothing else crosses the host.                              */
+typedef struct cs_b200_comm cs_b200_comm;
+
+/* rank 0: fill id128 (128 bytes) with a fresh NCCL unique id                                 */
+int cs_b200_comm_unique_id(void* id128);
+/* every rank: join the communicator on `device`                                              */
+int cs_b200_comm_init(int device, int rank, int nranks, const void* id128, cs_b200_comm** out);
+void cs_b200_comm_destroy(cs_b200_comm* c);
+const char* cs_b200_comm_last_error(const cs_b200_comm* c);
+
+/* cs_b200_create on every rank from the matrix held by `root` (arguments as cs_b200_create;
+ * rowptr / colidx / vals may be NULL on the other ranks, n / nnz / dtype / index_* must agree):
+ * the root uploads and narrows the CSR, one ncclBroadcast replicates it (and the root's
+ * aggregation seeds), every rank builds its own preconditioner from the device copy.          */
+int cs_b200_create_bcast(cs_b200_comm* c, int root, int64_t n, int64_t nnz, const void* rowptr,
+                         const void* colidx, const void* vals, int index_bits, int index_base,
+                         int dtype, const cs_b200_opts* opts, cs_b200_handle** out);
+
+/* end of job: cum <- SUM over ranks, max <- MAX over ranks, in place in every rank's handle
+ * (ncclAllReduce on the handle's solve stream, right behind the last accumulation kernel)     */
+int cs_b200_comm_reduce_currents(cs_b200_comm* c, cs_b200_handle* h);
+
+/* end of job: every rank contributes the resistances of its own pairs (global pair indices
+ * my_idx[k_mine], values my_R[k_mine], fp64) and receives all k_total of them in R_all
+ * (entries no rank contributed stay -1, the reference's "not solved" marker).                 */
+int cs_b200_comm_gather_pairs(cs_b200_comm* c, int64_t k_total, const int64_t* my_idx,
+                              int64_t k_mine, const double* my_R, double* R_all);
+
+/* max over ranks of a host double (timings) / sum of int64 counters                           */
+int cs_b200_comm_max_double(cs_b200_comm* c, double* v, int count);
+int cs_b200_comm_barrier(cs_b200_comm* c);
+
 /* Library/ABI version: major*1000 + minor.                                          */
 int cs_b200_version(void);
 
