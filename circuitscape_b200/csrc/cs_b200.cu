@@ -519,6 +519,14 @@ template <typename TV>
 int adopt_levels(cs_b200_handle* h, csb_dev::DHierarchy& hier, std::vector<DevLevel>& lv, bool own0) {
   const int nl = (int)hier.levels.size();
   lv.resize(nl);
+  Tick lt;
+  auto mark = [&](int l, const char* what) {
+    if (!lt.on) return;
+    cudaStreamSynchronize(h->stream);
+    char buf[64];
+    snprintf(buf, sizeof buf, "  L%d %s", l, what);
+    lt(buf);
+  };
   for (int l = 0; l < nl; ++l) {
     csb_dev::DLevel& hl = hier.levels[l];
     DevLevel& L = lv[l];
@@ -539,6 +547,7 @@ int adopt_levels(cs_b200_handle* h, csb_dev::DHierarchy& hier, std::vector<DevLe
       const bool win = h->opts.window > 0 || (L.n >= 20000 && (win_mask() & (l == 0 ? 1 : 2)));
       int rc = adopt_csr<TV>(h, hl.A, l == 0, L.A, win, (const TV*)L.dinv);
       if (rc) return rc;
+      mark(l, "A: copy/convert, blocks, windows");
       if (l > 0) {
         const size_t pe = (size_t)L.n_pad * h->ktmax * sizeof(TV);
         void** bufs[] = {&L.x, &L.b, &L.t, &L.y};
@@ -551,8 +560,10 @@ int adopt_levels(cs_b200_handle* h, csb_dev::DHierarchy& hier, std::vector<DevLe
     if (l + 1 < nl) {
       int rc = adopt_csr<TV>(h, hl.P, false, L.P, L.n >= 20000 && (win_mask() & 4), (const TV*)nullptr);
       if (rc) return rc;
+      mark(l, "P");
       rc = adopt_csr<TV>(h, hl.R, false, L.R, L.n >= 20000 && (win_mask() & 8), (const TV*)nullptr);
       if (rc) return rc;
+      mark(l, "R");
     }
   }
   return CS_B200_OK;
@@ -616,6 +627,8 @@ int setup_amg_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev:
     if (e != cudaSuccess) return done(set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (Z panel)", cudaGetErrorString(e)));
   }
   tick("levels: row blocks + windows");
+  csb_dev::coarse_pinv_wait(hier);
+  tick("coarse pseudo-inverse (wait)");
   const size_t nc = (size_t)hier.levels.back().A.nrows;
   if (hier.coarse_pinv.size() == nc * nc && nc > 0) {
     cudaError_t e = cudaMalloc(&h->d_pinv, nc * nc * sizeof(double));
@@ -630,12 +643,14 @@ template <typename T>
 int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job,
                         const csb_dev::DeviceSeed* dseed = nullptr) {
   h->A0 = DevCsr{h->d_rowptr, h->d_colidx, h->d_vals, nullptr, 0, (int)h->n, h->nnz, 1};
+  Tick tick0;
   int rc = device_row_blocks(h, h->A0, NT);
   if (rc) { csb_dev::seed_discard(job); return rc; }
   h->d_bstart = h->A0.bstart;
   h->nblocks = h->A0.nblocks;
   rc = alloc_common<T>(h);
   if (rc) { csb_dev::seed_discard(job); return rc; }
+  if (tick0.on) { cudaStreamSynchronize(h->stream); tick0("row blocks + panels"); }
   const bool want_win = h->opts.window >= 0 && (h->opts.window > 0 || h->n >= 20000) && (win_mask() & 1);
   const bool want_amg = h->opts.precond == CS_B200_PRECOND_AMG;
   Tick tick;
@@ -650,7 +665,9 @@ int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_d
   } else {
     csb_dev::seed_discard(job);
   }
+  Tick tick1;
   csb_dev::trim_pool(h->device);
+  tick1("scratch pool released");
   return cs_b200_reset_currents(h);
 }
 
@@ -1651,6 +1668,7 @@ int cs_b200_create(int64_t n, int64_t nnz, const void* rowptr, const void* colid
     }
     const csb_dev::HostPattern hp{rowptr, colidx, index_bits, index_base};
     csb_dev::SeedJob* job = nullptr;
+    Tick up_tick;
     if (h->opts.precond == CS_B200_PRECOND_AMG && n > 200) job = csb_dev::seed_start(n, hp);
     auto fail_job = [&](int code) { csb_dev::seed_discard(job); job = nullptr; return fail(code); };
 #define CKJ(call)                                                                              \
@@ -1681,7 +1699,7 @@ int cs_b200_create(int64_t n, int64_t nnz, const void* rowptr, const void* colid
     }
     CKJ(cudaMemcpyAsync(h->d_vals, vals, (size_t)nnz * es, cudaMemcpyHostToDevice, h->stream));
 #undef CKJ
-    { Tick tick; if (tick.on) { cudaStreamSynchronize(h->stream); tick("upload (narrowed on device)"); } }
+    if (up_tick.on) { cudaStreamSynchronize(h->stream); up_tick("upload (narrowed on device)"); }
     rc = dtype == CS_B200_F64 ? finish_setup_device<double>(h, hp, job) : finish_setup_device<float>(h, hp, job);
     if (rc) return fail(rc);
   } else {

@@ -556,7 +556,13 @@ void free_csr(DCsr& m) {
   m = DCsr{};
 }
 
+void coarse_pinv_wait(DHierarchy& h) {
+  if (h.pinv_job && h.pinv_job->valid()) h.coarse_pinv = h.pinv_job->get();
+  h.pinv_job.reset();
+}
+
 void free_hierarchy(DHierarchy& h) {
+  coarse_pinv_wait(h);
   for (auto& L : h.levels) {
     if (!L.borrowed) free_csr(L.A);
     free_csr(L.P);
@@ -741,8 +747,11 @@ int build_hierarchy(cudaStream_t s, const DCsr& A0, const HostPattern& hp0, Seed
       CKD(cudaMemcpyAsync(hc.val.data(), C.val, hc.val.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     CKD(cudaStreamSynchronize(s));
-    out.coarse_pinv = csb_amg::dense_pinv(hc);
-    tick("coarse pseudo-inverse", (int)out.levels.size() - 1);
+    // the dense eigen-solve (~0.1 s for 200 nodes on one core) runs on a helper thread while the
+    // caller turns the levels into window records; joined by coarse_pinv_wait()
+    out.pinv_job = std::make_shared<std::future<std::vector<double>>>(
+        std::async(std::launch::async, [hc = std::move(hc)]() { return csb_amg::dense_pinv(hc); }));
+    tick("coarse operator download", (int)out.levels.size() - 1);
   }
   double tot = 0.0;
   for (auto& L : out.levels) tot += (double)L.A.nnz;
@@ -752,39 +761,49 @@ int build_hierarchy(cudaStream_t s, const DCsr& A0, const HostPattern& hp0, Seed
 }
 
 // ---------------------------------------------------------------------------------------------
-// row blocks: next[r] = end of the greedy block that starts at row r; the blocks actually used are the
-// chain 0 -> next[0] -> next[next[0]] ... , found with pointer doubling (log2 n rounds)
+// row blocks: greedy blocks of <= max_rows rows and <= nnz_cap entries (a longer row stands alone), the
+// rule of win_host.hpp::row_blocks -- restarted at every chunk of CHUNK rows so that the chunks are
+// independent: one thread walks its chunk block by block (the end of a block is a binary search in
+// rowptr), first to count, then to write.  At most one short block per chunk more than the global
+// greedy partition (< 2 % for every operator of the hierarchy).
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-__global__ void k_next_block(int n, const int* __restrict__ rowptr, int max_rows, int cap, int* __restrict__ next,
-                             int* __restrict__ mark) {
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += gridDim.x * blockDim.x) {
-    mark[r] = r == 0 ? 1 : 0;
-    if (r == n) { next[r] = n; continue; }
-    const int base = rowptr[r];
-    int lo = r + 1, hi = min(n, r + max_rows);   // answer in [lo, hi]
-    // largest r1 with rowptr[r1] - base <= cap (rowptr is monotone); r + 1 if even one row overflows
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (rowptr[mid] - base <= cap) lo = mid; else hi = mid - 1;
+constexpr int RB_CHUNK = 2048;
+
+__device__ __forceinline__ int block_end(const int* __restrict__ rowptr, int r, int limit, int max_rows, int cap) {
+  const int base = rowptr[r];
+  int lo = r + 1, hi = min(limit, r + max_rows);   // answer in [lo, hi]
+  while (lo < hi) {                                 // largest r1 with rowptr[r1] - base <= cap
+    const int mid = (lo + hi + 1) >> 1;
+    if (rowptr[mid] - base <= cap) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void k_count_blocks(int n, const int* __restrict__ rowptr, int max_rows, int cap, int nchunk,
+                               int* __restrict__ cnt) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= nchunk; c += gridDim.x * blockDim.x) {
+    int k = 0;
+    if (c < nchunk) {
+      const int end = min(n, (c + 1) * RB_CHUNK);
+      for (int r = c * RB_CHUNK; r < end; ++k) r = block_end(rowptr, r, end, max_rows, cap);
     }
-    next[r] = lo;
+    cnt[c] = k;
   }
 }
 
-__global__ void k_mark_jump(int n, const int* __restrict__ jump, int* __restrict__ mark) {
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += gridDim.x * blockDim.x)
-    if (mark[r]) mark[jump[r]] = 1;
-}
-
-__global__ void k_double_jump(int n, const int* __restrict__ jump, int* __restrict__ jump2) {
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += gridDim.x * blockDim.x) jump2[r] = jump[jump[r]];
-}
-
-__global__ void k_scatter_marked(int n, const int* __restrict__ mark, const int* __restrict__ pos, int* __restrict__ bstart) {
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += gridDim.x * blockDim.x)
-    if (mark[r]) bstart[pos[r]] = r;     // row n is marked too: it lands in the last slot
+__global__ void k_write_blocks(int n, const int* __restrict__ rowptr, int max_rows, int cap, int nchunk,
+                               const int* __restrict__ off, int* __restrict__ bstart) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= nchunk; c += gridDim.x * blockDim.x) {
+    if (c == nchunk) { bstart[off[nchunk]] = n; continue; }
+    const int end = min(n, (c + 1) * RB_CHUNK);
+    int k = off[c];
+    for (int r = c * RB_CHUNK; r < end; ++k) {
+      bstart[k] = r;
+      r = block_end(rowptr, r, end, max_rows, cap);
+    }
+  }
 }
 
 }  // namespace
@@ -797,32 +816,22 @@ int row_blocks(cudaStream_t s, const int* d_rowptr, int64_t nrows, int max_rows,
   const int n = (int)nrows;
   *d_bstart = nullptr;
   *nblocks = 0;
-  Scratch<int> next, jump2, mark, pos;
-  CKD(next.alloc((size_t)n + 1, s));
-  CKD(jump2.alloc((size_t)n + 1, s));
-  CKD(mark.alloc((size_t)n + 2, s));
-  CKD(pos.alloc((size_t)n + 2, s));
-  const int g = grid_for((int64_t)n + 1);
-  k_next_block<<<g, TPB, 0, s>>>(n, d_rowptr, max_rows, nnz_cap, next.p, mark.p);
-  int* a = next.p;
-  int* b = jump2.p;
-  const int rounds = bits_for((int64_t)n + 2) + 1;
-  for (int t = 0; t < rounds; ++t) {
-    k_mark_jump<<<g, TPB, 0, s>>>(n, a, mark.p);
-    k_double_jump<<<g, TPB, 0, s>>>(n, a, b);
-    std::swap(a, b);
-  }
+  const int nchunk = (n + RB_CHUNK - 1) / RB_CHUNK;
+  Scratch<int> cnt, off;
+  CKD(cnt.alloc((size_t)nchunk + 1, s));
+  CKD(off.alloc((size_t)nchunk + 1, s));
+  const int g = grid_for((int64_t)nchunk + 1);
+  k_count_blocks<<<g, 64, 0, s>>>(n, d_rowptr, max_rows, nnz_cap, nchunk, cnt.p);
   CKD(cudaGetLastError());
-  CKD(cudaMemsetAsync(mark.p + n + 1, 0, sizeof(int), s));
-  int rc = exclusive_scan(s, mark.p, pos.p, (int64_t)n + 2, err);
+  int rc = exclusive_scan(s, cnt.p, off.p, (int64_t)nchunk + 1, err);
   if (rc) return rc;
-  int total = 0;   // marked rows incl. row n
-  CKD(cudaMemcpyAsync(&total, pos.p + n + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+  int total = 0;
+  CKD(cudaMemcpyAsync(&total, off.p + nchunk, sizeof(int), cudaMemcpyDeviceToHost, s));
   CKD(cudaStreamSynchronize(s));
-  CKD(cudaMalloc(d_bstart, (size_t)std::max(total, 1) * sizeof(int)));
-  k_scatter_marked<<<g, TPB, 0, s>>>(n, mark.p, pos.p, *d_bstart);
+  CKD(cudaMalloc(d_bstart, (size_t)(total + 1) * sizeof(int)));
+  k_write_blocks<<<g, 64, 0, s>>>(n, d_rowptr, max_rows, nnz_cap, nchunk, off.p, *d_bstart);
   CKD(cudaGetLastError());
-  *nblocks = total - 1;
+  *nblocks = total;
   return 0;
 }
 

@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <future>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -43,11 +45,13 @@ struct DLevel {
 
 struct DHierarchy {
   std::vector<DLevel> levels;
-  std::vector<double> coarse_pinv; // host, dense n_c x n_c (row-major); empty if n_c > 320
+  std::vector<double> coarse_pinv; // host, dense n_c x n_c (row-major); empty if n_c > 320 (after coarse_pinv_wait)
+  std::shared_ptr<std::future<std::vector<double>>> pinv_job;   // the eigen-solve, on a helper thread
   double operator_complexity = 1.0;
   double ms_agg_host = 0, ms_total = 0;
 };
 void free_hierarchy(DHierarchy& h);
+void coarse_pinv_wait(DHierarchy& h);   // joins the helper thread; fills coarse_pinv
 
 // Host copy of the finest pattern for the ordered aggregation pass (any index width / base, exactly
 // what the caller handed to cs_b200_create); null pointers => the pattern is downloaded.

@@ -155,7 +155,8 @@ def vcycle(ml, b, lvl=0):
 
 def pcg(A, b, ml, rtol=1e-6, atol=None, itmax=100_000, x0=None):
     """Preconditioned CG with Krylov.jl's `cg` stop rule.  Returns (x, iterations)."""
-    top = ml.levels[0] if ml is not None else Level(A)
+    # the hierarchy may have been built on a (regularised) copy: the operator applied is always A
+    top = ml.levels[0] if (ml is not None and A is ml.levels[0].A) else Level(A)
     if atol is None:
         atol = np.sqrt(np.finfo(np.float64).eps)
     n = len(b)
