@@ -33,7 +33,7 @@ class Opts(C.Structure):
     _fields_ = [("precond", C.c_int32), ("panel_width", C.c_int32), ("check_every", C.c_int32),
                 ("use_graph", C.c_int32), ("atol", C.c_double), ("resid_gate", C.c_double),
                 ("log_transform", C.c_int32), ("window", C.c_int32), ("mixed", C.c_int32), ("setup", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("stencil", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Stats(C.Structure):

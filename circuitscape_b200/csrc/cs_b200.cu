@@ -54,6 +54,10 @@ struct DevCsr {
   int has_dinv = 0;
   int64_t win_blocks = 0;
   int win_nblocks = 0;
+  // stencil (DIA) form (kernels.cuh k_stencil): 9 diagonals, ld apart; null => CSR kernels
+  void* dia = nullptr;
+  size_t dia_ld = 0;
+  int dia_nr = 0;
 };
 
 // one multigrid level below the finest (the finest level aliases the handle's own CSR)
@@ -231,8 +235,8 @@ int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowe
 }
 
 void free_win(DevCsr& d) {
-  cudaFree(d.win_meta); cudaFree(d.blob);
-  d.win_meta = nullptr; d.blob = nullptr;
+  cudaFree(d.win_meta); cudaFree(d.blob); cudaFree(d.dia);
+  d.win_meta = nullptr; d.blob = nullptr; d.dia = nullptr;
 }
 
 void free_csr(DevCsr& d) {
@@ -471,6 +475,23 @@ int device_windows(cs_b200_handle* h, DevCsr& d, int64_t ncols_pad, const T* d_d
   return CS_B200_OK;
 }
 
+// stencil (DIA) form of a square operator, if its pattern allows it (opts.stencil: 0 auto, 1, -1 never)
+template <typename T>
+int device_stencil(cs_b200_handle* h, DevCsr& d) {
+  static const bool env_off = std::getenv("CS_B200_NO_STENCIL") != nullptr;
+  if (h->opts.stencil < 0 || env_off) return CS_B200_OK;
+  if (h->opts.stencil == 0 && d.nrows < 20000) return CS_B200_OK;
+  T* dia = nullptr;
+  int nr = 0;
+  size_t ld = 0;
+  int rc = csb_dev::build_dia<T>(h->stream, d.rowptr, d.colidx, (const T*)d.vals, d.nrows, &dia, &nr, &ld, h->err);
+  if (rc) return rc_dev(h, rc);
+  d.dia = dia;
+  d.dia_nr = nr;
+  d.dia_ld = ld;
+  return CS_B200_OK;
+}
+
 // take over a hierarchy operator as a device CSR of TV: the index arrays move (or are duplicated when
 // the source is the handle's own matrix), the fp64 values move or are converted
 template <typename TV>
@@ -508,6 +529,11 @@ int adopt_csr(cs_b200_handle* h, csb_dev::DCsr& src, bool duplicate, DevCsr& d, 
   max_rows = std::min(NT, std::max(unit, (max_rows + unit - 1) / unit * unit));
   int rc = device_row_blocks(h, d, max_rows);
   if (rc) return rc;
+  if (src.nrows == src.ncols && d_dinv != nullptr) {   // square level operator: stencil form if it has one
+    rc = device_stencil<TV>(h, d);
+    if (rc) return rc;
+    if (d.dia) return CS_B200_OK;
+  }
   if (h->opts.window >= 0 && windowed) {
     const int64_t ncols_pad = (src.ncols + 3) / 4 * 4;
     return device_windows<TV>(h, d, ncols_pad, d_dinv);
@@ -655,9 +681,10 @@ int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_d
   const bool want_amg = h->opts.precond == CS_B200_PRECOND_AMG;
   Tick tick;
   if (want_win) {
-    rc = device_windows<T>(h, h->A0, h->n_pad, (const T*)h->d_dinv);
+    rc = device_stencil<T>(h, h->A0);
+    if (!rc && !h->A0.dia) rc = device_windows<T>(h, h->A0, h->n_pad, (const T*)h->d_dinv);
     if (rc) { csb_dev::seed_discard(job); return rc; }
-    tick("finest operator: windows");
+    tick(h->A0.dia ? "finest operator: stencil form" : "finest operator: windows");
   }
   if (want_amg) {
     rc = setup_amg_device<T>(h, hp, job, dseed);
@@ -745,7 +772,18 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
     cudaEventRecord(e0, h->stream);
   }
   const SpmmEpi<T> ep{B, dinv, (T)omega, h->d_ctl, h->d_partials};
-  if (m.win_meta) {
+  if (m.dia && MODE != SP_ADD) {
+    if constexpr (MODE != SP_ADD) {
+      const DiaDev<T> a{(const T*)m.dia, m.dia_ld, m.nrows, m.dia_nr};
+      constexpr int V16 = 16 / (int)sizeof(T);
+      constexpr int CGn = KT / (KT < V16 ? KT : V16);
+      const int rpp = NT / CGn;
+      const long long ntiles = (long long)((m.dia_nr + rpp - 1) / rpp) *
+                               ((((long long)m.nrows + m.dia_nr - 1) / m.dia_nr + ST_TC - 1) / ST_TC);
+      const int sg = (int)std::max<long long>(1, std::min<long long>(h->grid_spmm, ntiles));
+      k_stencil<T, KT, MODE><<<sg, NT, 0, h->stream>>>(a, X, Y, ep);
+    }
+  } else if (m.win_meta) {
     const WinCsr<T> w{m.win_meta, m.blob, m.has_dinv, m.rowptr, m.colidx, (const T*)m.vals, m.win_nblocks};
     if (m.lpr == 4) {
       constexpr int SMEM = WinSmem2<T, KT, MODE, true>::TOTAL;
@@ -1851,7 +1889,7 @@ int cs_b200_level_info(cs_b200_handle* h, int level, int which, int64_t* nrows, 
   if (ncols) *ncols = nc;
   if (nnz) *nnz = m->nnz;
   if (omega) *omega = om;
-  if (windowed) *windowed = m->win_meta ? 1 : 0;
+  if (windowed) *windowed = m->dia ? 2 : (m->win_meta ? 1 : 0);   // 2 = stencil (DIA) form
   return CS_B200_OK;
 }
 

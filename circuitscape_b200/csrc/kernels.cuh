@@ -918,6 +918,140 @@ k_spmm_win(const WinCsr<T> A, const T* __restrict__ X, T* __restrict__ Y, const 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Stencil (DIA) SpMM: Y = op(A X) for an operator whose every stored entry (i, j) has
+// j - i in {0, +-1, +-nr, +-(nr -+ 1)} for one stride nr -- the 5-/9-point raster stencil of the
+// reference with its column-major node numbering (src/raster/pairwise.jl:316-367) whenever
+// every cell of the raster is a node, and the Galerkin operators of the regular coarse grids
+// below it.  Found at setup (setup_device.cu build_dia); the operator is then stored as 9
+// diagonals, slot-major (vals[s * ld + i], s = 3 * (dc + 1) + (dr + 1)): no column stream, no
+// row offsets -- 9 s_v bytes per row instead of 9 (s_v + 4) + 4 of CSR.
+//
+// A CTA owns a tile of RPP consecutive rows of one raster column x TC consecutive raster
+// columns and sweeps the columns left to right; thread (row, column group) issues its 9
+// coalesced value loads and 9 panel-row gathers (one 16-byte vector each) before the first FMA.
+// The +-1 neighbours sit in the lines the warp's own rows fetch, the +-nr strips of column c are
+// the centre strips of columns c -+ 1 of the same tile (L1) or of the neighbouring tile, which
+// the round-robin tile order keeps in flight at the same time (L2).  Same epilogues / same
+// deterministic reductions as k_spmm / k_spmm_win.
+// ---------------------------------------------------------------------------
+template <typename T> struct DiaDev {
+  const T* vals;   // 9 diagonals, ld apart
+  size_t ld;
+  int n;
+  int nr;          // stride between raster columns
+};
+
+constexpr int ST_TC = 16;   // raster columns per tile
+
+template <typename T, int KT, int MODE>
+__global__ void __launch_bounds__(NT)
+k_stencil(const DiaDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
+  constexpr int V16 = 16 / (int)sizeof(T);
+  constexpr int CPT = KT < V16 ? KT : V16;      // panel columns per thread (one 16-byte vector)
+  constexpr int CG = KT / CPT;                  // column groups per row
+  constexpr int RPP = NT / CG;                  // rows per pass of the CTA
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, rl = tid / CG, c0 = cg * CPT;
+  const int n = A.n, nr = A.nr;
+  const int ncol = (n + nr - 1) / nr;           // raster columns
+  const int nrc = (nr + RPP - 1) / RPP;         // row chunks per raster column
+  const int ntc = (ncol + ST_TC - 1) / ST_TC;   // column groups
+  const long long ntiles = (long long)nrc * ntc;
+  double dot0[CPT], dot1[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) dot0[i] = dot1[i] = 0.0;
+
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tc = (int)(t / nrc), rc = (int)(t % nrc);
+    const int r = rc * RPP + rl;                // row within the raster column
+    if (r >= nr) continue;
+    const int cend = min(ncol, (tc + 1) * ST_TC);
+    for (int c = tc * ST_TC; c < cend; ++c) {
+      const long long row_l = (long long)c * nr + r;
+      if (row_l >= n) break;
+      const int row = (int)row_l;
+      T v[9];
+#pragma unroll
+      for (int s = 0; s < 9; ++s) v[s] = ld_stream(A.vals + (size_t)s * A.ld + row);
+      T xv[9][CPT];
+#pragma unroll
+      for (int s = 0; s < 9; ++s) {
+        // missing neighbours carry a zero value: any in-range row will do for the gather
+        int j = row + (s / 3 - 1) * nr + (s % 3 - 1);
+        j = max(0, min(n - 1, j));
+        ldvec<T, CPT>(X + (size_t)j * KT + c0, xv[s]);
+      }
+      T acc[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) acc[i] = T(0);
+#pragma unroll
+      for (int s = 0; s < 9; ++s)
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) acc[i] += v[s] * xv[s][i];
+      const size_t o = (size_t)row * KT + c0;
+      T out[CPT], bb[CPT];
+      constexpr bool NEEDB = (MODE == SP_RESNORM || MODE == SP_RES || MODE == SP_JACOBI || MODE == SP_JACOBI_DOT);
+      if (NEEDB) ldvec<T, CPT>(ep.B + o, bb);
+      T dv = T(0);
+      if (MODE == SP_JACOBI || MODE == SP_JACOBI_DOT) dv = ep.omega * ep.dinv[row];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        const T xo = xv[4][i];
+        if (MODE == SP_PLAIN) {
+          out[i] = acc[i];
+        } else if (MODE == SP_CG) {
+          out[i] = acc[i];
+          dot0[i] += (double)acc[i] * (double)xo;
+        } else if (MODE == SP_RESNORM) {
+          const T rr = bb[i] - acc[i];
+          out[i] = rr;
+          dot0[i] += (double)rr * (double)rr;
+          dot1[i] += (double)bb[i] * (double)bb[i];
+        } else if (MODE == SP_RES) {
+          out[i] = bb[i] - acc[i];
+        } else {
+          const T yn = xo + dv * (bb[i] - acc[i]);
+          out[i] = yn;
+          if (MODE == SP_JACOBI_DOT) dot0[i] += (double)bb[i] * (double)yn;
+        }
+      }
+      stvec<T, CPT>(Y + o, out);
+    }
+  }
+  if (MODE == SP_CG) {
+    CSB_REDUCE_SMEM(1, KT)
+    double v[1][CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) v[0][i] = dot0[i];
+    if (grid_reduce<KT, CPT, 1, false>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
+      if (tid < KT) {
+        const double pap = s_out[tid];
+        ep.ctl->pap[tid] = pap;
+        ep.ctl->alpha[tid] = (ep.ctl->active[tid] && pap > 0.0) ? ep.ctl->rho[tid] / pap : 0.0;
+      }
+    }
+  } else if (MODE == SP_RESNORM) {
+    CSB_REDUCE_SMEM(2, KT)
+    double v[2][CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { v[0][i] = dot0[i]; v[1][i] = dot1[i]; }
+    if (grid_reduce<KT, CPT, 2, false>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out)) {
+      if (tid < KT) {
+        ep.ctl->resid[tid] = s_out[tid];
+        ep.ctl->bnorm[tid] = s_out[KT + tid];
+      }
+    }
+  } else if (MODE == SP_JACOBI_DOT) {
+    CSB_REDUCE_SMEM(1, KT)
+    double v[1][CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) v[0][i] = dot0[i];
+    if (grid_reduce<KT, CPT, 1, false>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out))
+      cg_after_precond<KT>(ep.ctl, s_out);
+  }
+}
+
 // Build the per-block records of the windowed form on the device: one CTA per block copies
 // the values (through the host-built permutation), the 16-bit local columns and the row
 // offsets into  blob + blob_off16*16 :  [ values nnzp | lcol nnzp | roff roffp ].

@@ -1044,6 +1044,85 @@ int build_windowed(cudaStream_t s, const int* d_rowptr, const int* d_colidx, con
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// stencil (DIA) detection + fill
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+template <typename T>
+__global__ void k_dia_fill(int n, int nr, size_t ld, const int* __restrict__ ptr, const int* __restrict__ idx,
+                           const T* __restrict__ val, T* __restrict__ dia, int* __restrict__ bad) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    T d[9];
+#pragma unroll
+    for (int s = 0; s < 9; ++s) d[s] = T(0);
+    int miss = 0;
+    for (int j = ptr[i]; j < ptr[i + 1]; ++j) {
+      const int off = idx[j] - i;
+      int s = -1;
+      if (off >= -1 && off <= 1) s = 4 + off;
+      else if (off >= nr - 1 && off <= nr + 1) s = 7 + (off - nr);
+      else if (-off >= nr - 1 && -off <= nr + 1) s = 1 + (off + nr);
+      if (s < 0) { miss = 1; continue; }
+      const T v = val[j];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) if (q == s) d[q] += v;
+    }
+#pragma unroll
+    for (int s = 0; s < 9; ++s) dia[(size_t)s * ld + i] = d[s];
+    if (miss) atomicOr(bad, 1);
+  }
+}
+
+}  // namespace
+
+template <typename T>
+int build_dia(cudaStream_t s, const int* d_rowptr, const int* d_colidx, const T* d_vals, int64_t n, T** d_dia, int* nr,
+              size_t* ld, std::string& err) {
+  *d_dia = nullptr;
+  *nr = 0;
+  *ld = 0;
+  if (n < 16) return 0;
+  // stride candidate from row 0: its first column beyond 1 (row 0 of a raster has neighbours 1, nr, nr + 1)
+  int rp[2] = {0, 0};
+  CKD(cudaMemcpyAsync(rp, d_rowptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CKD(cudaStreamSynchronize(s));
+  const int len = rp[1] - rp[0];
+  if (len < 2 || len > 9) return 0;
+  int cols[9];
+  CKD(cudaMemcpyAsync(cols, d_colidx + rp[0], (size_t)len * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CKD(cudaStreamSynchronize(s));
+  int stride = 0;
+  for (int q = 0; q < len; ++q)
+    if (cols[q] > 1 && (stride == 0 || cols[q] < stride)) stride = cols[q];
+  if (stride < 3 || stride >= n) return 0;
+  const size_t l = ((size_t)n + 3) / 4 * 4;
+  T* dia = nullptr;
+  Scratch<int> bad;
+  CKD(bad.alloc(1, s));
+  CKD(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+  CKD(cudaMalloc(&dia, 9 * l * sizeof(T)));
+  cudaMemsetAsync(dia, 0, 9 * l * sizeof(T), s);
+  k_dia_fill<T><<<grid_for(n), TPB, 0, s>>>((int)n, stride, l, d_rowptr, d_colidx, d_vals, dia, bad.p);
+  int hb = 1;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    cudaFree(dia);
+    err = std::string("CUDA error ") + cudaGetErrorString(e) + " building the stencil form";
+    return -2;
+  }
+  if (hb) { cudaFree(dia); return 0; }
+  *d_dia = dia;
+  *nr = stride;
+  *ld = l;
+  return 0;
+}
+
+template int build_dia<float>(cudaStream_t, const int*, const int*, const float*, int64_t, float**, int*, size_t*, std::string&);
+template int build_dia<double>(cudaStream_t, const int*, const int*, const double*, int64_t, double**, int*, size_t*, std::string&);
+
 template int build_windowed<float>(cudaStream_t, const int*, const int*, const float*, int64_t, int64_t, int, const float*,
                                    DWin&, std::string&);
 template int build_windowed<double>(cudaStream_t, const int*, const int*, const double*, int64_t, int64_t, int,

@@ -103,6 +103,15 @@ template <typename T>
 int build_windowed(cudaStream_t stream, const int* d_rowptr, const int* d_colidx, const T* d_vals, int64_t nrows,
                    int64_t ncols_pad, int wcap, const T* d_dinv, DWin& out, std::string& err);
 
+// Stencil (DIA) form of a square device CSR: if every stored entry (i, j) has j - i in
+// {0, +-1, +-nr, +-(nr -+ 1)} for one stride nr >= 3 (the raster stencil with column-major numbering,
+// src/raster/pairwise.jl:316-367, and the regular coarse grids below it), *d_dia receives the 9
+// diagonals (slot s = 3 (dc + 1) + (dr + 1), ld = n rounded up to 4, zero where there is no entry;
+// cudaMalloc'ed) and *nr the stride; otherwise *d_dia stays null.
+template <typename T>
+int build_dia(cudaStream_t stream, const int* d_rowptr, const int* d_colidx, const T* d_vals, int64_t n, T** d_dia,
+              int* nr, size_t* ld, std::string& err);
+
 // narrow caller indices (int32 / int64, base 0 / 1) to int32 0-based on the device
 int narrow_indices(cudaStream_t stream, const void* d_src, int index_bits, int index_base, int64_t count, int* d_dst);
 int convert_values(cudaStream_t stream, const double* d_in, float* d_out, int64_t count);

@@ -42,6 +42,7 @@ class CUDASolver:
     window: str = "auto"             # TMA-staged windowed SpMM: auto | on | off
     f32_compute: bool = False        # precision = single: keep fp32 ON THE DEVICE too (see B200Factor)
     mixed: bool = True               # fp64 + AMG: fp32 V-cycle inside fp64 CG
+    stencil: str = "auto"            # stencil (DIA) SpMM on full-raster operators: auto | on | off
     setup: str = "auto"              # hierarchy / window records built: auto (device) | device | host
     superpose: bool = False          # pairwise driver: one solve per focal NODE, pairs by superposition
     batch_all_to_one: bool = False   # all-to-one: every iteration a column of ONE batch on one operator
@@ -106,6 +107,7 @@ class B200Factor:
         opts.window = {"auto": 0, "on": 1, "off": -1}[solver.window]
         opts.mixed = 0 if solver.mixed else -1
         opts.setup = {"auto": 0, "host": 1, "device": 2}[solver.setup]
+        opts.stencil = {"auto": 0, "on": 1, "off": -1}[solver.stencil]
         return opts
 
     @classmethod
@@ -165,7 +167,8 @@ class B200Factor:
                            self._lib.cs_b200_level_csr(self._h, l, which, _lib._ptr(rp), _lib._ptr(ci), _lib._ptr(va)))
                 lev[name] = sp.csr_matrix((va, ci, rp), shape=(nr.value, nc.value))
                 lev["omega"] = om.value
-                lev[name + "_windowed"] = bool(win.value)
+                lev[name + "_windowed"] = bool(win.value)        # TMA-window records or stencil form
+                lev[name + "_stencil"] = win.value == 2
             if lev["A"] is None:
                 break
             out.append(lev)

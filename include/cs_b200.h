@@ -77,7 +77,10 @@ typedef struct cs_b200_opts {
   int32_t setup;          /* where the multigrid hierarchy and the windowed records are built:
                              0 auto (on the device), 1 on the host (amg_host.hpp / win_host.hpp,
                              the round-1 path, kept for A/B checks), 2 on the device           */
-  int32_t reserved[4];
+  int32_t stencil;        /* stencil (DIA) SpMM for operators whose entries all sit on the 9 raster
+                             diagonals (full rasters, regular coarse grids): 0 auto (operators
+                             >= 20000 rows), 1 always, -1 never                                */
+  int32_t reserved[3];
 } cs_b200_opts;
 
 /* Per-call statistics (milliseconds measured with CUDA events on the solve stream). */

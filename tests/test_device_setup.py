@@ -216,3 +216,54 @@ def test_c_program_links_and_solves(tmp_path):
         r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, (args, r.stdout, r.stderr)
         assert "R0=" in r.stdout
+
+
+# ---- stencil (DIA) form: SURVEY.md 8f rank 2 ------------------------------------------------------
+@pytest.mark.parametrize("four", [False, True])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_stencil_form_spmm(dtype, four):
+    """Full raster (every cell a node): the operator is stored as 9 diagonals and multiplied by
+    k_stencil; every panel width against SciPy, first / last raster columns and rows included."""
+    A = graph.synthetic_raster_laplacian(233, 171, seed=5, four_neighbors=four)[0].tocsr()
+    n = A.shape[0]
+    prec = "single" if dtype == np.float32 else "double"
+    rng = np.random.default_rng(4)
+    with cb.B200Factor(A, cb.CUDASolver(precision=prec, f32_compute=True, precond="jacobi", stencil="on")) as f:
+        for k in (1, 2, 4, 8):
+            X = rng.standard_normal((n, k))
+            Y = f.spmm(X)
+            ref = A.astype(dtype) @ X.astype(dtype)
+            tol = (1e-13 if dtype == np.float64 else 3e-6) * np.abs(A).sum(axis=1).max() * np.abs(X).max()
+            assert np.abs(Y - ref).max() <= tol, k
+        y, _ = f.spmv(X[:, 0])
+        assert np.abs(y - A.astype(dtype) @ X[:, 0].astype(dtype)).max() <= tol
+
+
+@pytest.mark.parametrize("mixed", [True, False])
+def test_stencil_form_solve_matches_csr_kernels(mixed):
+    """Same iteration counts and resistances with the stencil kernels (level 0 and the regular coarse
+    grids that qualify) as with the windowed / plain CSR kernels; a raster with NODATA holes has no
+    stencil form and silently keeps the CSR path."""
+    A = graph.synthetic_raster_laplacian(260, 240, seed=9)[0]
+    nodes = graph.focal_nodes(A.shape[0], 6, seed=7)
+    src, dst = graph.all_pairs(nodes)
+    out = {}
+    for st in ("auto", "off"):
+        with cb.B200Factor(A, cb.CUDASolver(stencil=st, mixed=mixed)) as f:
+            out[st] = f.solve_pairs(src, dst, accumulate=True), f.read_currents()[0]
+            lv = f.levels()
+            assert lv[0]["A_stencil"] == (st == "auto")
+    (a, ca), (b, cb_) = out["auto"], out["off"]
+    assert np.array_equal(a["iters"], b["iters"])
+    assert np.abs(a["R"] - b["R"]).max() <= 1e-9 * np.abs(b["R"]).max()
+    assert np.abs(ca - cb_).max() <= 1e-8 * np.abs(cb_).max()
+    Vref = co.solve_pairs_direct(A, src[:3], dst[:3])
+    assert np.abs(a["R"][:3] - Vref[dst[:3], np.arange(3)]).max() <= 1e-6 * a["R"][:3].max()
+    H = holey(200, 180, 5, holes=0.03)
+    with cb.B200Factor(H, cb.CUDASolver(stencil="on")) as f:
+        assert not f.levels()[0]["A_stencil"]
+        nodes = graph.focal_nodes(H.shape[0], 3, seed=7)
+        s2, d2 = graph.all_pairs(nodes)
+        o = f.solve_pairs(s2, d2)
+    V2 = co.solve_pairs_direct(H, s2, d2)
+    assert np.abs(o["R"] - V2[d2, np.arange(len(s2))]).max() <= 1e-6 * o["R"].max()
