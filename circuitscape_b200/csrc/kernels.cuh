@@ -945,7 +945,7 @@ template <typename T> struct DiaDev {
 constexpr int ST_TC = 16;   // raster columns per tile
 
 template <typename T, int KT, int MODE>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 k_stencil(const DiaDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
   constexpr int V16 = 16 / (int)sizeof(T);
   constexpr int CPT = KT < V16 ? KT : V16;      // panel columns per thread (one 16-byte vector)
@@ -973,7 +973,7 @@ k_stencil(const DiaDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const S
       const int row = (int)row_l;
       T v[9];
 #pragma unroll
-      for (int s = 0; s < 9; ++s) v[s] = ld_stream(A.vals + (size_t)s * A.ld + row);
+      for (int s = 0; s < 9; ++s) v[s] = __ldcs(A.vals + (size_t)s * A.ld + row);   // streamed once: evict first
       T xv[9][CPT];
 #pragma unroll
       for (int s = 0; s < 9; ++s) {

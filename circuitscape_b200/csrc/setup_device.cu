@@ -96,6 +96,25 @@ struct Tick {
   }
 };
 
+// CS_B200_VERBOSE=2: host time between sub-steps (stream synchronised), to find non-kernel overheads
+struct Stamp {
+  bool on;
+  cudaStream_t s;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit Stamp(cudaStream_t st) : s(st) {
+    const char* e = std::getenv("CS_B200_VERBOSE");
+    on = e && std::atoi(e) >= 2;
+  }
+  void operator()(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[cs_b200 setup/stamp]        %-34s %8.2f ms\n", what,
+                 std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------
@@ -393,11 +412,13 @@ int spgemm(cudaStream_t s, const DCsr& A, const DCsr& B, int64_t product_budget,
   *overflow = false;
   C = DCsr{};
   C.nrows = A.nrows; C.ncols = B.ncols;
+  Stamp st(s);
   Scratch<int> erow;
   Scratch<long long> cnt, off;
   CKD(erow.alloc((size_t)A.nnz, s));
   CKD(cnt.alloc((size_t)A.nnz + 1, s));
   CKD(off.alloc((size_t)A.nnz + 1, s));
+  st("spgemm: scratch alloc");
   k_fill_erow<<<grid_for(A.nrows), TPB, 0, s>>>((int)A.nrows, A.ptr, erow.p);
   k_cnt_products<<<grid_for(A.nnz + 1), TPB, 0, s>>>(A.nnz, A.idx, B.ptr, cnt.p);
   CKD(cudaGetLastError());
@@ -406,6 +427,7 @@ int spgemm(cudaStream_t s, const DCsr& A, const DCsr& B, int64_t product_budget,
   long long m = 0;
   CKD(cudaMemcpyAsync(&m, off.p + A.nnz, sizeof(long long), cudaMemcpyDeviceToHost, s));
   CKD(cudaStreamSynchronize(s));
+  st("spgemm: count + scan");
   if (m > product_budget || m >= (long long)std::numeric_limits<int>::max()) {
     *overflow = true;
     return 0;
@@ -418,12 +440,16 @@ int spgemm(cudaStream_t s, const DCsr& A, const DCsr& B, int64_t product_budget,
   CKD(k1.alloc((size_t)m, s));
   CKD(v0.alloc((size_t)m, s));
   CKD(v1.alloc((size_t)m, s));
+  st("spgemm: item buffers alloc");
   k_expand_AB<<<grid_for(A.nnz), TPB, 0, s>>>(A.nnz, erow.p, A.idx, A.val, B.ptr, B.idx, B.val, off.p, cb, k0.p, v0.p);
   CKD(cudaGetLastError());
+  st("spgemm: expand");
   rc = sort_pairs(s, k0.p, k1.p, v0.p, v1.p, m, cb + rb, err);
   if (rc) return rc;
+  st("spgemm: sort");
   k0.release();
   v0.release();
+  struct Tail { Stamp& st; ~Tail() { st("spgemm: compress"); } } tail{st};
   return compress_to_csr(s, m, k1.p, v1.p, A.nrows, B.ncols, cb, false, 0, max_nnz, overflow, C, err);
 }
 

@@ -175,6 +175,14 @@ class B200Factor:
             l += 1
         return out
 
+    def operator_form(self):
+        """'stencil' (9 diagonals, k_stencil), 'windowed' (TMA-staged CSR records, k_spmm_win) or
+        'csr' (plain row-block kernel) for the finest operator the CG SpMM runs on."""
+        win = C.c_int()
+        rc = self._lib.cs_b200_level_info(self._h, 0, 0, None, None, None, None, C.byref(win))
+        _lib.check(self._lib, self._h, rc)
+        return {2: "stencil", 1: "windowed"}.get(win.value, "csr")
+
     # -- lifetime ---------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

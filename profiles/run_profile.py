@@ -16,7 +16,7 @@ from circuitscape_b200 import graph  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=3163)
-ap.add_argument("--what", default="spmm", choices=["spmm", "cg", "solve"])
+ap.add_argument("--what", default="spmm", choices=["spmm", "cg", "cg8", "solve"])
 ap.add_argument("--precision", default="double")
 ap.add_argument("--precond", default="jacobi")
 ap.add_argument("--no-mixed", action="store_true")
@@ -31,6 +31,9 @@ with cb.construct_cholesky_factor(L, cb.CUDASolver(precision=a.precision, precon
             ms = f.bench_spmm(k, reps=a.reps, flush_l2=True)
             b = nnz * (sv + 4) + (n + 1) * 4 + 2 * n * k * sv
             print(f"spmm k={k}: {ms:.4f} ms  {b / ms / 1e6:.1f} GB/s (algorithmic {b} B)")
+    elif a.what == "cg8":          # one k = 8 AMG-PCG iteration only (short ncu captures)
+        ms = f.bench_cg_iter(8, reps=a.reps)
+        print(f"cg_iter k=8: {ms:.4f} ms")
     elif a.what == "cg":
         for k in (1, 8):
             ms = f.bench_cg_iter(k, reps=a.reps)
