@@ -58,6 +58,7 @@ _PROTOS = {
                                              C.POINTER(Opts), C.POINTER(_H), C.POINTER(C.c_int64),
                                              C.POINTER(C.c_int64)]),
     "cs_b200_get_csr": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_b200_set_grounds": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "cs_b200_level_info": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "cs_b200_level_csr": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -449,9 +449,26 @@ class AdvancedOutput:
     branch: tuple | None = None
 
 
-def multiple_solver(cfg, solver, a, sources, grounds, finitegrounds):
+def multiple_solver(cfg, solver, a, sources, grounds, finitegrounds, resident=None):
     """src/raster/advanced.jl:274-305: diag += finite grounds; rows/cols of Inf
-    grounds deleted (0 V); `multiple_solve`; zeros re-inserted."""
+    grounds deleted (0 V); `multiple_solve`; zeros re-inserted.
+
+    resident = (cache dict, key): keep ONE device factor of the component's Laplacian `a` under `key`
+    and move the grounds on the device (cs_b200_set_grounds: identity rows instead of deleted ones)
+    -- for the one-to-all / all-to-one loops, where only the grounds change between iterations."""
+    if resident is not None:
+        cache, key = resident
+        f = cache.get(key)
+        if f is None:
+            f = cache[key] = S.construct_cholesky_factor(sp.csr_matrix(a, dtype=np.float64), solver)
+        mask = np.asarray(grounds) == np.inf
+        f.set_grounds(None if finitegrounds[0] == NODATA else np.asarray(finitegrounds, dtype=np.float64),
+                      mask if mask.any() else None)
+        b = np.asarray(sources, dtype=np.float64).copy()
+        b[mask] = 0.0
+        v = np.asarray(S.solve_linear_system(f, a, b), dtype=np.float64).copy()   # residual gate inside (hook #2)
+        v[mask] = 0.0
+        return v
     a = sp.csr_matrix(a, dtype=np.float64)
     n = a.shape[0]
     if finitegrounds[0] != NODATA:
@@ -809,6 +826,7 @@ def onetoall_kernel(data: RasterData, flags: Flags, cfg, solver=None, one_to_all
     if one_to_all and inc is None and getattr(solver, "batch_one_to_all", False):
         batched1 = _one_to_all_batched_raster(G, comps, nodemap, newpoly, point_map, unique_point_map, uniq,
                                               rr, cc_, strengths, solver)
+    resident_factors = {}          # CUDASolver(resident_grounds=True): one device factor per component
     for i, n in enumerate(uniq):
         pm, nm, npoly = point_map.copy(), nodemap, newpoly
         if inc is not None:
@@ -873,7 +891,9 @@ def onetoall_kernel(data: RasterData, flags: Flags, cfg, solver=None, one_to_all
                 continue
             fl = f_[rows] if f_[0] != NODATA else f_
             a_local = G[rows][:, rows].tocsr()
-            v = multiple_solver(cfg, solver, a_local, sl, gl, fl)
+            v = multiple_solver(cfg, solver, a_local, sl, gl, fl,
+                                resident=(resident_factors, tuple(rows[:2]) + (len(rows),))
+                                if getattr(solver, "resident_grounds", False) else None)
             out.num_solves += 1
             lm = construct_local_node_map(nm, np.asarray(comp), npoly)
             called = True
@@ -894,6 +914,8 @@ def onetoall_kernel(data: RasterData, flags: Flags, cfg, solver=None, one_to_all
         out.cum_curmap += outcurr
         if out.max_curmap is not None:
             out.max_curmap = np.maximum(out.max_curmap, outcurr)
+    for f in resident_factors.values():
+        f.close()
     out.resistances = np.column_stack([uniq, res])
     out.cum_curmap = np.where(out.cum_curmap < NODATA, NODATA, out.cum_curmap)
     return out

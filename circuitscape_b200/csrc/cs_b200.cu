@@ -77,6 +77,7 @@ struct cs_b200_handle {
   int* d_colidx = nullptr;
   void* d_vals = nullptr;
   bool owns_matrix = true;
+  void* d_vals0 = nullptr;           // pristine values while grounds are applied (cs_b200_set_grounds)
   void* d_dinv = nullptr;
   int* d_bstart = nullptr;
   int nblocks = 0;
@@ -682,6 +683,10 @@ int setup_amg_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev:
 }
 
 template <typename T>
+int build_operators(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job,
+                    const csb_dev::DeviceSeed* dseed);
+
+template <typename T>
 int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job,
                         const csb_dev::DeviceSeed* dseed = nullptr) {
   h->A0 = DevCsr{h->d_rowptr, h->d_colidx, h->d_vals, nullptr, 0, (int)h->n, h->nnz, 1};
@@ -693,6 +698,19 @@ int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_d
   rc = alloc_common<T>(h);
   if (rc) { csb_dev::seed_discard(job); return rc; }
   if (tick0.on) { cudaStreamSynchronize(h->stream); tick0("row blocks + panels"); }
+  rc = build_operators<T>(h, hp, job, dseed);
+  if (rc) return rc;
+  return cs_b200_reset_currents(h);
+}
+
+// 1/diag, the finest operator's stencil / window form, the multigrid hierarchy: everything that depends
+// on the matrix VALUES (re-run by cs_b200_set_grounds after the values changed)
+template <typename T>
+int build_operators(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_dev::SeedJob* job,
+                    const csb_dev::DeviceSeed* dseed) {
+  int rc = CS_B200_OK;
+  k_dinv<T><<<std::min<int64_t>((h->n_pad + 255) / 256, 4096), 256, 0, h->stream>>>(
+      (int)h->n, (int)h->n_pad, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (T*)h->d_dinv);
   const bool want_win = h->opts.window >= 0 && (h->opts.window > 0 || h->n >= 20000) && (win_mask() & 1);
   const bool want_amg = h->opts.precond == CS_B200_PRECOND_AMG;
   Tick tick;
@@ -711,7 +729,7 @@ int finish_setup_device(cs_b200_handle* h, const csb_dev::HostPattern& hp, csb_d
   Tick tick1;
   csb_dev::trim_pool(h->device);
   tick1("scratch pool released");
-  return cs_b200_reset_currents(h);
+  return CS_B200_OK;
 }
 
 int common_create(cs_b200_handle* h, const cs_b200_opts* opts) {
@@ -1672,6 +1690,61 @@ int assemble_raster(cs_b200_handle* h, int64_t nrows, int64_t ncols, const T* g_
 
 }  // namespace
 
+namespace {
+template <typename T>
+__global__ void k_apply_grounds(int n, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                T* __restrict__ vals, const T* __restrict__ g, const unsigned char* __restrict__ mask) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool mi = mask && mask[i];
+    for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+      const int c = colidx[j];
+      if (mi) vals[j] = c == i ? T(1) : T(0);
+      else if (mask && mask[c]) vals[j] = T(0);
+      else if (c == i && g) vals[j] += g[i];
+    }
+  }
+}
+}  // namespace
+
+// everything derived from the operator's VALUES: captured graphs (they hold level pointers), the
+// finest operator's stencil / window records, the multigrid levels.  The CSR, the plain row blocks
+// and the panels stay.
+static void teardown_operators(cs_b200_handle* h) {
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& g : h->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.loop_exec) cudaGraphExecDestroy(g.loop_exec);
+    g = GraphSlot{};
+  }
+  free_win(h->A0);
+  h->A0.has_dinv = 0; h->A0.win_blocks = 0; h->A0.win_nblocks = 0; h->A0.dia_nr = 0; h->A0.dia_ld = 0;
+  for (size_t l = 0; l < h->lv.size(); ++l) {
+    DevLevel& L = h->lv[l];
+    if (l > 0) {
+      free_csr(L.A);
+      cudaFree(L.dinv); cudaFree(L.x); cudaFree(L.b); cudaFree(L.t); cudaFree(L.y);
+    }
+    free_csr(L.P);
+    free_csr(L.R);
+  }
+  for (size_t l = 0; l < h->lv32.size(); ++l) {
+    DevLevel& L = h->lv32[l];
+    free_csr(L.A);
+    cudaFree(L.dinv); cudaFree(L.x); cudaFree(L.b); cudaFree(L.t); cudaFree(L.y);
+    free_csr(L.P);
+    free_csr(L.R);
+  }
+  h->lv.clear();
+  h->lv32.clear();
+  cudaFree(h->R32); cudaFree(h->X32); cudaFree(h->T32); cudaFree(h->Z32);
+  h->R32 = h->X32 = h->T32 = h->Z32 = nullptr;
+  cudaFree(h->Z); h->Z = nullptr;
+  cudaFree(h->d_pinv); h->d_pinv = nullptr;
+  h->amg = false;
+  h->mixed = false;
+}
+
+
 extern "C" {
 
 int cs_b200_version(void) { return 1001; }
@@ -1938,6 +2011,62 @@ int cs_b200_level_csr(cs_b200_handle* h, int level, int which, int32_t* rowptr, 
   return CS_B200_OK;
 }
 
+int cs_b200_set_grounds(cs_b200_handle* h, const void* finite_g, const uint8_t* dirichlet) {
+  if (!h) return CS_B200_ERR_ARG;
+  if (h->opts.setup == 1)
+    return set_err(h, CS_B200_ERR_UNSUPPORTED, "cs_b200_set_grounds needs the device-side setup (opts.setup != 1)");
+  if (!h->owns_matrix)
+    return set_err(h, CS_B200_ERR_UNSUPPORTED, "cs_b200_set_grounds: the handle borrows its matrix (create_from_device)");
+  cudaSetDevice(h->device);
+  h->err.clear();
+  const size_t es = h->esize();
+  const size_t vb = std::max<size_t>(1, (size_t)h->nnz) * es;
+  cudaEventRecord(h->ev0, h->stream);
+  if (!h->d_vals0) {
+    CK(h, cudaMalloc(&h->d_vals0, vb));
+    CK(h, cudaMemcpyAsync(h->d_vals0, h->d_vals, vb, cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    CK(h, cudaMemcpyAsync(h->d_vals, h->d_vals0, vb, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  void* d_g = nullptr;
+  unsigned char* d_m = nullptr;
+  auto cleanup = [&]() { cudaFree(d_g); cudaFree(d_m); };
+  if (finite_g) {
+    cudaError_t e = cudaMalloc(&d_g, (size_t)h->n * es);
+    if (e == cudaSuccess) e = h2d(h, d_g, finite_g, (size_t)h->n * es);
+    if (e != cudaSuccess) { cleanup(); return set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (finite grounds)", cudaGetErrorString(e)); }
+  }
+  if (dirichlet) {
+    cudaError_t e = cudaMalloc(&d_m, (size_t)h->n);
+    if (e == cudaSuccess) e = h2d(h, d_m, dirichlet, (size_t)h->n);
+    if (e != cudaSuccess) { cleanup(); return set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (Dirichlet mask)", cudaGetErrorString(e)); }
+  }
+  if (finite_g || dirichlet) {
+    const int g = (int)std::min<int64_t>((h->n + 255) / 256, (int64_t)h->num_sms * 32);
+    if (h->dtype == CS_B200_F64)
+      k_apply_grounds<double><<<g, 256, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx, (double*)h->d_vals,
+                                                        (const double*)d_g, d_m);
+    else
+      k_apply_grounds<float><<<g, 256, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx, (float*)h->d_vals,
+                                                       (const float*)d_g, d_m);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (e != cudaSuccess) return set_err(h, CS_B200_ERR_CUDA, "CUDA error %s applying the grounds", cudaGetErrorString(e));
+  teardown_operators(h);
+  const csb_dev::HostPattern none{};
+  int rc = h->dtype == CS_B200_F64 ? build_operators<double>(h, none, nullptr, nullptr)
+                                   : build_operators<float>(h, none, nullptr, nullptr);
+  if (rc) return rc;
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.setup_ms = ms;
+  return CS_B200_OK;
+}
+
 int cs_b200_get_dims(const cs_b200_handle* h, int64_t* n, int64_t* nnz) {
   if (!h) return CS_B200_ERR_ARG;
   if (n) *n = h->n;
@@ -1948,32 +2077,9 @@ int cs_b200_get_dims(const cs_b200_handle* h, int64_t* n, int64_t* nnz) {
 void cs_b200_destroy(cs_b200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
-  for (auto& g : h->graphs) {
-    if (g.exec) cudaGraphExecDestroy(g.exec);
-    if (g.loop_exec) cudaGraphExecDestroy(g.loop_exec);
-  }
+  teardown_operators(h);
   if (h->owns_matrix) { cudaFree(h->d_rowptr); cudaFree(h->d_colidx); cudaFree(h->d_vals); }
-  free_win(h->A0);
-  for (size_t l = 0; l < h->lv.size(); ++l) {
-    DevLevel& L = h->lv[l];
-    if (l > 0) {
-      free_csr(L.A);
-      cudaFree(L.dinv); cudaFree(L.x); cudaFree(L.b); cudaFree(L.t); cudaFree(L.y);
-    }
-    free_csr(L.P);
-    free_csr(L.R);
-  }
-  for (size_t l = 0; l < h->lv32.size(); ++l) {
-    DevLevel& L = h->lv32[l];
-    free_csr(L.A);
-    cudaFree(L.dinv); cudaFree(L.x); cudaFree(L.b); cudaFree(L.t); cudaFree(L.y);
-    free_csr(L.P);
-    free_csr(L.R);
-  }
-  cudaFree(h->R32); cudaFree(h->X32); cudaFree(h->T32); cudaFree(h->Z32);
-  cudaFree(h->Z);
-  cudaFree(h->d_pinv);
+  cudaFree(h->d_vals0);
   void* bufs[] = {h->d_dinv, h->d_bstart, h->X, h->R, h->P, h->AP, h->B, h->stage,
                   h->d_cum, h->d_max, h->d_ctl, h->d_partials, h->d_flush};
   for (void* b : bufs) if (b) cudaFree(b);

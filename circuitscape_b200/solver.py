@@ -47,6 +47,8 @@ class CUDASolver:
     superpose: bool = False          # pairwise driver: one solve per focal NODE, pairs by superposition
     batch_all_to_one: bool = False   # all-to-one: every iteration a column of ONE batch on one operator
     batch_one_to_all: bool = False   # one-to-all: one solve per iteration on ONE grounded operator
+    resident_grounds: bool = False   # advanced mode: keep the component's factor, move the grounds on the
+                                     # device (cs_b200_set_grounds) instead of a new handle per solve
 
     @property
     def dtype(self):
@@ -174,6 +176,16 @@ class B200Factor:
             out.append(lev)
             l += 1
         return out
+
+    def set_grounds(self, finite=None, dirichlet=None):
+        """cs_b200_set_grounds: re-derive the operator on the device as  G + diag(finite)  with the rows /
+        columns of the `dirichlet` nodes replaced by identity rows (src/raster/advanced.jl:274-305) and
+        rebuild the preconditioner; (None, None) restores the pristine operator."""
+        g = None if finite is None else np.ascontiguousarray(finite, dtype=self.dtype)
+        m = None if dirichlet is None else np.ascontiguousarray(np.asarray(dirichlet) != 0, dtype=np.uint8)
+        assert g is None or len(g) == self.n
+        assert m is None or len(m) == self.n
+        _lib.check(self._lib, self._h, self._lib.cs_b200_set_grounds(self._h, _lib._ptr(g), _lib._ptr(m)))
 
     def operator_form(self):
         """'stencil' (9 diagonals, k_stencil), 'windowed' (TMA-staged CSR records, k_spmm_win) or

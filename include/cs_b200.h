@@ -130,6 +130,19 @@ int cs_b200_create_from_raster(int64_t nrows, int64_t ncols, const void* g, int 
  * of n+1, nnz and nnz elements; any pointer may be NULL.  Parity / debugging hook.            */
 int cs_b200_get_csr(cs_b200_handle* h, int32_t* rowptr, int32_t* colidx, void* vals);
 
+/* Advanced mode on a RESIDENT operator (src/raster/advanced.jl:274-305): the reference rebuilds
+ * `G + diag(finite grounds)` with the rows / columns of the Inf grounds deleted for every solve; here
+ * the handle keeps the component's Laplacian and this call re-derives the operator on the device:
+ *     finite_g  (n values of the handle's dtype, or NULL)   added to the diagonal
+ *     dirichlet (n bytes, non-zero = tied to ground, or NULL) row and column replaced by the identity
+ *                                                           row -- the deleted row with its 0 V kept in place
+ * then 1/diag, the stencil / window records and the multigrid hierarchy are rebuilt from the device-
+ * resident CSR (no matrix crosses PCIe; ~0.1 s at 10^6 nodes).  Right-hand sides passed afterwards must
+ * be zero at the Dirichlet rows (the reference drops those sources).  Calling it again starts from the
+ * pristine values; NULL, NULL restores the original operator.  Needs the device-side setup and a
+ * handle that owns its matrix.                                                                    */
+int cs_b200_set_grounds(cs_b200_handle* h, const void* finite_g, const uint8_t* dirichlet);
+
 /* Multigrid hierarchy inspection (parity / debugging hooks; levels exist only with the AMG
  * preconditioner).  which: 0 = operator A_l, 1 = prolongator P_l (level l <- l+1), 2 = restriction
  * R_l = P_l^T.  level_info returns CS_B200_ERR_ARG past the last level (and for P / R on the

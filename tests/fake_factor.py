@@ -18,6 +18,20 @@ class FakeFactor:
         self.dtype = np.dtype(np.float64)
         self.reset_currents()
 
+    def set_grounds(self, finite=None, dirichlet=None):
+        """CPU double of cs_b200_set_grounds: diag += finite, identity rows at the Dirichlet nodes."""
+        if not hasattr(self, "A0"):
+            self.A0 = self.A.copy()
+        A = self.A0.tolil(copy=True)
+        if finite is not None:
+            A.setdiag(A.diagonal() + np.asarray(finite, dtype=np.float64))
+        if dirichlet is not None:
+            m = np.nonzero(np.asarray(dirichlet))[0]
+            A = A.tocsr()
+            keep = sp.diags((~np.asarray(dirichlet, dtype=bool)).astype(np.float64))
+            A = (keep @ A @ keep + sp.diags(np.asarray(dirichlet, dtype=np.float64))).tolil()
+        self.A = sp.csr_matrix(A)
+
     def __enter__(self):
         return self
 

@@ -494,3 +494,46 @@ def test_golden_network_pairwise_windowed_log(golden, i):
                                                       cb.CUDASolver(rtol=1e-8, window="on"))
     flags.outputflags.log_transform_maps = True
     cases.check_network_pairwise(cb.single_ground_all_pairs(prob, flags), exp)
+
+
+# ---- device-resident grounds (cs_b200_set_grounds) -------------------------------------------------
+def test_set_grounds_matches_scipy_on_the_modified_system():
+    """finite grounds on the diagonal + Dirichlet rows, against SciPy's direct solve of the reference's
+    reduced system (src/raster/advanced.jl:274-305); repeated calls start from the pristine operator and
+    (None, None) restores the singular Laplacian."""
+    import scipy.sparse.linalg as spla
+    A = holey_raster(160, 150, seed=12)
+    n = A.shape[0]
+    rng = np.random.default_rng(5)
+    with cb.B200Factor(A, cb.CUDASolver(rtol=1e-10)) as f:
+        for trial in range(3):
+            fg = np.zeros(n)
+            fg[rng.choice(n, 5, replace=False)] = rng.uniform(0.1, 2.0, 5)
+            mask = np.zeros(n, dtype=bool)
+            mask[rng.choice(n, 4, replace=False)] = True
+            b = np.zeros(n)
+            b[rng.choice(np.nonzero(~mask)[0], 6, replace=False)] = rng.uniform(0.5, 2.0, 6)
+            f.set_grounds(fg if trial != 1 else None, mask)
+            x, iters, relres = f.solve_rhs(b)
+            M = (A + sp.diags(fg if trial != 1 else np.zeros(n))).tocsr()
+            keep = np.nonzero(~mask)[0]
+            ref = np.zeros(n)
+            ref[keep] = spla.splu(M[keep][:, keep].tocsc()).solve(b[keep])
+            assert relres.max() < 1e-4 and iters.max() < 200
+            assert np.abs(x - ref).max() <= 1e-7 * np.abs(ref).max(), trial
+            assert np.all(x[mask] == 0.0)
+        f.set_grounds(None, None)                        # pristine singular operator again
+        nodes = graph.focal_nodes(n, 3, seed=7)
+        src, dst = graph.all_pairs(nodes)
+        o = f.solve_pairs(src, dst)
+    Vref = co.solve_pairs_direct(A, src, dst)
+    assert np.abs(o["R"] - Vref[dst, np.arange(len(src))]).max() <= 1e-7 * o["R"].max()
+
+
+@pytest.mark.parametrize("name", [f"oneToAllVerify{i}" for i in (1, 4, 10, 13)] + [f"allToOneVerify{i}" for i in (1, 7, 12)])
+def test_golden_onetoall_resident_grounds(golden, name):
+    data, flags, cfg, exp = cases.onetoall_problem(golden, name)
+    fl = co.cfg_flags(cfg)
+    r = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(rtol=1e-8, resident_grounds=True),
+                           four_neighbors=fl["four_neighbors"], avg_res=fl["avg_res"])
+    cases.check_onetoall(r, exp, flags)

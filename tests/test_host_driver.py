@@ -263,3 +263,15 @@ def test_sink_streams_maps_instead_of_keeping_them(golden):
     nsink = _Sink()
     r = cb.single_ground_all_pairs(prob, flags, sink=nsink)
     assert not r.curmaps and not r.branch and nsink.net
+
+
+@pytest.mark.parametrize("name", ONE_TO_ALL)
+def test_onetoall_driver_resident_grounds(golden, name):
+    """CUDASolver(resident_grounds=True): one factor per component kept across the iterations of the
+    one-to-all / all-to-one loop, the grounds moved by set_grounds (identity rows instead of deleted
+    rows, src/raster/advanced.jl:274-305); same goldens."""
+    data, flags, cfg, exp = cases.onetoall_problem(golden, name)
+    fl = co.cfg_flags(cfg)
+    r = cb.onetoall_kernel(data, flags, cfg, solver=cb.CUDASolver(resident_grounds=True),
+                           four_neighbors=fl["four_neighbors"], avg_res=fl["avg_res"])
+    cases.check_onetoall(r, exp, flags)

@@ -18,7 +18,9 @@ TOL = 1e-6
 
 
 @pytest.fixture(autouse=True)
-def fake_device(monkeypatch):
+def fake_device(monkeypatch, request):
+    if "gpu" in request.keywords:            # the gpu-marked tests write files from REAL device results
+        return
     monkeypatch.setattr(S, "construct_cholesky_factor", lambda m, s, **kw: FakeFactor(m, s, **kw))
     monkeypatch.setattr(S, "multiple_solve", lambda s, m, b: FakeFactor(m, s).solve_rhs(np.asarray(b))[0])
 
@@ -41,7 +43,11 @@ def read_table(path):
 
 @pytest.mark.parametrize("name", ["sgVerify1", "sgVerify3", "sgVerify12"])
 def test_raster_pairwise_files(golden, name, tmp_path):
-    r, exp = cases.run_raster_pairwise(golden, name, cb.CUDASolver())
+    _raster_files(golden, tmp_path, name, cb.CUDASolver())
+
+
+def _raster_files(golden, tmp_path, name, solver):
+    r, exp = cases.run_raster_pairwise(golden, name, solver)
     cfg, inp, _ = co.load_case(golden, name)
     shape = inp["habitat_file"][1].shape
     meta = O.RasterMeta(ncols=shape[1], nrows=shape[0], xllcorner=3.5, yllcorner=-2.0, cellsize=0.25)
@@ -70,7 +76,11 @@ def test_raster_pairwise_files(golden, name, tmp_path):
 
 
 def test_network_pairwise_files(golden, tmp_path):
-    prob, flags, exp = cases.network_pairwise_problem(golden, "sgNetworkVerify1", cb.CUDASolver())
+    _network_files(golden, tmp_path, cb.CUDASolver())
+
+
+def _network_files(golden, tmp_path, solver):
+    prob, flags, exp = cases.network_pairwise_problem(golden, "sgNetworkVerify1", solver)
     r = cb.single_ground_all_pairs(prob, flags)
     of = str(tmp_path / "net.out")
     O.write_pairwise_outputs(r, of, None)
@@ -102,3 +112,47 @@ def test_grid_names_and_number_format(tmp_path):
     assert np.array_equal(a, b)                         # repr-exact floats survive the round trip
     with pytest.raises(ValueError):
         O.write_asc(str(tmp_path / "h.asc"), a.T, m)
+
+
+# ---- the same file-level checks with results that came from the CUDA library -------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sgVerify1", "sgVerify2", "sgVerify5", "sgVerify9", "sgVerify14", "sgVerify16"])
+def test_raster_pairwise_files_from_device_results(golden, tmp_path, name):
+    """device results -> the reference's file set -> read back -> goldens"""
+    _raster_files(golden, tmp_path, name, cb.CUDASolver(rtol=1e-8))
+
+
+@pytest.mark.gpu
+def test_network_pairwise_files_from_device_results(golden, tmp_path):
+    _network_files(golden, tmp_path, cb.CUDASolver(rtol=1e-8))
+
+
+@pytest.mark.gpu
+def test_streaming_sink_writes_the_same_files_from_device_results(golden, tmp_path):
+    """maps handed to a writer sink as each batch finishes (nothing kept in memory) give the files
+    the keep-everything path gives"""
+    name = "sgVerify1"
+    kept, _ = cases.run_raster_pairwise(golden, name, cb.CUDASolver(rtol=1e-8))
+    shape = co.load_case(golden, name)[1]["habitat_file"][1].shape
+    meta = O.RasterMeta(ncols=shape[1], nrows=shape[0], xllcorner=0.0, yllcorner=0.0, cellsize=1.0)
+    a = str(tmp_path / "a" / f"{name}.out")
+    b = str(tmp_path / "b" / f"{name}.out")
+    os.makedirs(os.path.dirname(b))
+    O.write_pairwise_outputs(kept, a, meta)
+
+    class Sink:
+        def voltmap(self, key, grid):
+            O.write_grid(grid, f"_{key[0]}_{key[1]}", b, meta, voltage=True)
+
+        def curmap(self, key, grid):
+            O.write_grid(grid, f"_{key[0]}_{key[1]}", b, meta)
+
+    streamed, _ = cases.run_raster_pairwise(golden, name, cb.CUDASolver(rtol=1e-8), sink=Sink())
+    assert not streamed.curmaps and not streamed.voltmaps
+    pa, pb = os.path.dirname(a), os.path.dirname(b)
+    maps = sorted(f for f in os.listdir(pb) if f.endswith(".asc"))
+    assert maps
+    for f in maps:
+        ga, _ = read_asc(os.path.join(pa, f))
+        gb, _ = read_asc(os.path.join(pb, f))
+        assert np.array_equal(ga, gb), f
