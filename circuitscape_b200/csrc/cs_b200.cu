@@ -1943,6 +1943,96 @@ int cs_b200_create_from_raster(int64_t nrows, int64_t ncols, const void* g, int 
   return CS_B200_OK;
 }
 
+int cs_b200_create_from_raster_poly(int64_t nrows, int64_t ncols, const void* g, const int32_t* polymap,
+                                    int dtype, int four_neighbors, int avg_res, int device,
+                                    const cs_b200_opts* opts, cs_b200_handle** out, int64_t* n_out,
+                                    int64_t* nnz_out, int32_t* nodemap_out) {
+  if (!out) return set_err(nullptr, CS_B200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (nrows <= 0 || ncols <= 0 || !g || (dtype != CS_B200_F32 && dtype != CS_B200_F64) ||
+      nrows > (int64_t)1 << 30 || ncols > (int64_t)1 << 30)
+    return set_err(nullptr, CS_B200_ERR_ARG, "bad arguments");
+  if (nrows * ncols * 17 >= (int64_t)1 << 31)
+    return set_err(nullptr, CS_B200_ERR_UNSUPPORTED, "raster too large: 17 * cells must be < 2^31 (device indices are int32)");
+  const int64_t ncell = nrows * ncols;
+  int max_poly = 0;
+  if (polymap) {
+    for (int64_t i = 0; i < ncell; ++i) {
+      if (polymap[i] < 0) return set_err(nullptr, CS_B200_ERR_ARG, "polygon ids must be >= 0 (cell %lld holds %d)", (long long)i, polymap[i]);
+      max_poly = std::max(max_poly, (int)polymap[i]);
+    }
+    if (max_poly > (1 << 27)) return set_err(nullptr, CS_B200_ERR_UNSUPPORTED, "polygon ids above 2^27 are not supported");
+  }
+  cs_b200_handle* h = new cs_b200_handle();
+  h->n = 0; h->nnz = 0; h->dtype = dtype; h->device = device;
+  h->owns_matrix = true;
+  int rc = common_create(h, opts);
+  auto fail = [&](int code) { g_create_error = h->err; cs_b200_destroy(h); return code; };
+  if (rc) return fail(rc);
+  cudaEventRecord(h->ev0, h->stream);
+  double* d_g = nullptr;
+  int* d_poly = nullptr;
+  int* d_node = nullptr;
+  void* d_raw = nullptr;
+  csb_dev::DCsr L;
+  auto cleanup = [&]() { cudaFree(d_g); cudaFree(d_poly); cudaFree(d_node); cudaFree(d_raw); };
+  cudaError_t e = cudaMalloc(&d_g, (size_t)ncell * sizeof(double));
+  if (e == cudaSuccess && dtype == CS_B200_F64) e = h2d(h, d_g, g, (size_t)ncell * sizeof(double));
+  if (e == cudaSuccess && dtype == CS_B200_F32) {
+    e = cudaMalloc(&d_raw, (size_t)ncell * sizeof(float));
+    if (e == cudaSuccess) e = h2d(h, d_raw, g, (size_t)ncell * sizeof(float));
+    if (e == cudaSuccess) e = (cudaError_t)csb_dev::convert_values(h->stream, (const float*)d_raw, d_g, ncell);
+  }
+  if (e == cudaSuccess && polymap) {
+    e = cudaMalloc(&d_poly, (size_t)ncell * sizeof(int));
+    if (e == cudaSuccess) e = h2d(h, d_poly, polymap, (size_t)ncell * sizeof(int));
+  }
+  if (e != cudaSuccess) { cleanup(); set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (raster upload)", cudaGetErrorString(e)); return fail(CS_B200_ERR_CUDA); }
+  rc = csb_dev::assemble_raster_polygons(h->stream, nrows, ncols, d_g, d_poly, max_poly, four_neighbors ? 1 : 0,
+                                         avg_res ? 1 : 0, L, &d_node, h->err);
+  if (rc) { cleanup(); return fail(rc == -1 ? CS_B200_ERR_ARG : rc_dev(h, rc)); }
+  h->n = L.nrows;
+  h->nnz = L.nnz;
+  h->n_pad = (h->n + 3) / 4 * 4;
+  h->d_rowptr = L.ptr;
+  h->d_colidx = L.idx;
+  if (dtype == CS_B200_F64) {
+    h->d_vals = L.val;
+  } else {
+    e = cudaMalloc(&h->d_vals, std::max<size_t>(1, (size_t)L.nnz) * sizeof(float));
+    if (e == cudaSuccess) e = (cudaError_t)csb_dev::convert_values(h->stream, L.val, (float*)h->d_vals, L.nnz);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(L.val);
+    if (e != cudaSuccess) { cleanup(); set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (value conversion)", cudaGetErrorString(e)); return fail(CS_B200_ERR_CUDA); }
+  }
+  if (nodemap_out) {
+    e = cudaMemcpyAsync(nodemap_out, d_node, (size_t)ncell * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { cleanup(); set_err(h, CS_B200_ERR_CUDA, "CUDA error %s (node map download)", cudaGetErrorString(e)); return fail(CS_B200_ERR_CUDA); }
+  }
+  cleanup();
+  if (h->opts.setup != 1) {
+    const csb_dev::HostPattern hp{};
+    rc = dtype == CS_B200_F64 ? finish_setup_device<double>(h, hp, nullptr) : finish_setup_device<float>(h, hp, nullptr);
+  } else {
+    std::vector<int> rp((size_t)h->n + 1);
+    e = cudaMemcpy(rp.data(), h->d_rowptr, rp.size() * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_err(h, CS_B200_ERR_CUDA, "CUDA error %s reading rowptr", cudaGetErrorString(e)); return fail(CS_B200_ERR_CUDA); }
+    rc = dtype == CS_B200_F64 ? finish_setup<double>(h, rp, nullptr, (const double*)nullptr)
+                              : finish_setup<float>(h, rp, nullptr, (const float*)nullptr);
+  }
+  if (rc) return fail(rc);
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.setup_ms = ms;
+  if (n_out) *n_out = h->n;
+  if (nnz_out) *nnz_out = h->nnz;
+  *out = h;
+  return CS_B200_OK;
+}
+
 int cs_b200_get_csr(cs_b200_handle* h, int32_t* rowptr, int32_t* colidx, void* vals) {
   if (!h) return CS_B200_ERR_ARG;
   cudaSetDevice(h->device);

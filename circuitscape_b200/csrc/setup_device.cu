@@ -130,6 +130,11 @@ __global__ void k_cvt(const TI* __restrict__ in, TO* __restrict__ out, int64_t c
     out[i] = (TO)in[i];
 }
 
+__global__ void k_fill_int(int* p, int64_t count, int v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
 __global__ void k_zero_int(int* p, int64_t count) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = 0;
@@ -1143,6 +1148,170 @@ int build_dia(cudaStream_t s, const int* d_rowptr, const int* d_colidx, const T*
   *d_dia = dia;
   *nr = stride;
   *ld = l;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// raster assembly with short-circuit polygons
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ double stencil_weight(double a, double b, bool diagonal, bool avg_res) {
+  const double s2 = 1.4142135623730951;                    // src/raster/pairwise.jl:364-367
+  if (avg_res) return diagonal ? 1.0 / (s2 * (1.0 / a + 1.0 / b) / 2.0) : 1.0 / ((1.0 / a + 1.0 / b) / 2.0);
+  return diagonal ? (a + b) / (2.0 * s2) : (a + b) / 2.0;
+}
+
+__global__ void k_poly_valid(int64_t ncell, const double* __restrict__ g, int* __restrict__ valid) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= ncell; i += (int64_t)gridDim.x * blockDim.x)
+    valid[i] = (i < ncell && g[i] > 0.0) ? 1 : 0;
+}
+
+__global__ void k_poly_rep(int64_t ncell, const int* __restrict__ poly, const int* __restrict__ valid,
+                           int* __restrict__ rep) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x)
+    if (poly[i] > 0 && valid[i]) atomicMin(&rep[poly[i]], (int)i);      // first valid cell in memory order
+}
+
+// label = own rank among the valid cells (1-based), or the representative's for polygon cells
+__global__ void k_poly_label(int64_t ncell, const int* __restrict__ poly, const int* __restrict__ valid,
+                             const int* __restrict__ vrank, const int* __restrict__ rep, int* __restrict__ label,
+                             int* __restrict__ used) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x) {
+    int l = valid[i] ? vrank[i] + 1 : 0;
+    if (poly && poly[i] > 0) {
+      const int r = rep[poly[i]];
+      if (r != 0x7fffffff) l = vrank[r] + 1;
+    }
+    label[i] = l;
+    if (l) used[l] = 1;
+  }
+}
+
+__global__ void k_poly_node(int64_t ncell, const int* __restrict__ label, const int* __restrict__ newid,
+                            int* __restrict__ node) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x)
+    node[i] = label[i] ? newid[label[i]] + 1 : 0;
+}
+
+// pass 0: items per cell (1 diagonal placeholder + 2 per adjacency to another node) ; pass 1: emit
+template <int PASS>
+__global__ void k_poly_items(int nrows, int ncols, int four, int avg_res, const double* __restrict__ g,
+                             const int* __restrict__ node, long long* __restrict__ cnt, const long long* __restrict__ off,
+                             int cb, unsigned long long* __restrict__ keys, double* __restrict__ vals) {
+  const int64_t ncell = (int64_t)nrows * ncols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell + (PASS == 0 ? 1 : 0);
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i == ncell) { cnt[i] = 0; continue; }
+    const int a = node[i];
+    long long k = 0;
+    if (a) {
+      const int r = (int)(i % nrows), c = (int)(i / nrows);
+      const double gi = g[i] > 0.0 ? g[i] : 0.0;
+      long long o = PASS ? off[i] : 0;
+      const unsigned long long hi = (unsigned long long)(a - 1) << cb;
+      if (PASS) { keys[o] = hi | (unsigned)(a - 1); vals[o] = 0.0; ++o; }   // every node has a diagonal entry
+      k = 1;
+      for (int q = 0; q < 9; ++q) {
+        if (q == 4) continue;
+        const int dr = q % 3 - 1, dc = q / 3 - 1;
+        const bool diagonal = dr != 0 && dc != 0;
+        if (four && diagonal) continue;
+        const int rr = r + dr, cc = c + dc;
+        if (rr < 0 || rr >= nrows || cc < 0 || cc >= ncols) continue;
+        const int64_t j = (int64_t)cc * nrows + rr;
+        const int b = node[j];
+        if (!b || b == a) continue;                          // inside one node: dropped by laplacian!
+        if (PASS) {
+          const double gj = g[j] > 0.0 ? g[j] : 0.0;
+          const double w = stencil_weight(gi, gj, diagonal, avg_res != 0);
+          keys[o] = hi | (unsigned)(b - 1); vals[o] = -w; ++o;
+          keys[o] = hi | (unsigned)(a - 1); vals[o] = w; ++o;
+        }
+        k += 2;
+      }
+    }
+    if (!PASS) cnt[i] = k;
+  }
+}
+
+}  // namespace
+
+int assemble_raster_polygons(cudaStream_t s, int64_t nrows, int64_t ncols, const double* d_g, const int* d_poly,
+                             int max_poly, int four, int avg_res, DCsr& out, int** d_nodemap, std::string& err) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  ensure_pool(dev);
+  out = DCsr{};
+  *d_nodemap = nullptr;
+  const int64_t ncell = nrows * ncols;
+  const int g = grid_for(ncell + 1);
+  Scratch<int> valid, vrank, rep, label, used, newid;
+  CKD(valid.alloc((size_t)ncell + 1, s));
+  CKD(vrank.alloc((size_t)ncell + 1, s));
+  CKD(label.alloc((size_t)ncell, s));
+  k_poly_valid<<<g, TPB, 0, s>>>(ncell, d_g, valid.p);
+  CKD(cudaGetLastError());
+  int rc = exclusive_scan(s, valid.p, vrank.p, ncell + 1, err);
+  if (rc) return rc;
+  int nvalid = 0;
+  CKD(cudaMemcpyAsync(&nvalid, vrank.p + ncell, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CKD(cudaStreamSynchronize(s));
+  if (nvalid <= 0) { err = "raster has no cell with conductance > 0"; return -1; }
+  if (d_poly) {
+    CKD(rep.alloc((size_t)max_poly + 1, s));
+    k_fill_int<<<grid_for(max_poly + 1), TPB, 0, s>>>(rep.p, (int64_t)max_poly + 1, 0x7fffffff);   // "no valid cell"
+    k_poly_rep<<<g, TPB, 0, s>>>(ncell, d_poly, valid.p, rep.p);
+  }
+  CKD(used.alloc((size_t)nvalid + 2, s));
+  CKD(newid.alloc((size_t)nvalid + 2, s));
+  k_zero_int<<<grid_for(nvalid + 2), TPB, 0, s>>>(used.p, nvalid + 2);
+  k_poly_label<<<g, TPB, 0, s>>>(ncell, d_poly, valid.p, vrank.p, rep.p, label.p, used.p);
+  CKD(cudaGetLastError());
+  rc = exclusive_scan(s, used.p, newid.p, (int64_t)nvalid + 2, err);
+  if (rc) return rc;
+  int nnode = 0;
+  CKD(cudaMemcpyAsync(&nnode, newid.p + nvalid + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CKD(cudaStreamSynchronize(s));
+  int* node = nullptr;
+  CKD(cudaMalloc(&node, (size_t)ncell * sizeof(int)));
+  k_poly_node<<<g, TPB, 0, s>>>(ncell, label.p, newid.p, node);
+  valid.release(); vrank.release(); label.release(); used.release(); newid.release(); rep.release();
+  // items -> sort -> CSR
+  Scratch<long long> cnt, off;
+  cudaError_t e = cnt.alloc((size_t)ncell + 1, s);
+  if (e == cudaSuccess) e = off.alloc((size_t)ncell + 1, s);
+  if (e != cudaSuccess) { cudaFree(node); CKD(e); }
+  const int cb = bits_for(nnode);
+  k_poly_items<0><<<g, TPB, 0, s>>>((int)nrows, (int)ncols, four, avg_res, d_g, node, cnt.p, nullptr, cb, nullptr, nullptr);
+  rc = exclusive_scan(s, cnt.p, off.p, ncell + 1, err);
+  long long m = 0;
+  if (!rc) {
+    e = cudaMemcpyAsync(&m, off.p + ncell, sizeof(long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { err = std::string("CUDA error ") + cudaGetErrorString(e); rc = -2; }
+  }
+  if (!rc && m >= (long long)std::numeric_limits<int>::max()) { err = "raster too large for int32 entry counts"; rc = -5; }
+  if (rc) { cudaFree(node); return rc; }
+  cnt.release();
+  Scratch<unsigned long long> k0, k1;
+  Scratch<double> v0, v1;
+  e = k0.alloc((size_t)m, s);
+  if (e == cudaSuccess) e = k1.alloc((size_t)m, s);
+  if (e == cudaSuccess) e = v0.alloc((size_t)m, s);
+  if (e == cudaSuccess) e = v1.alloc((size_t)m, s);
+  if (e != cudaSuccess) { cudaFree(node); CKD(e); }
+  k_poly_items<1><<<g, TPB, 0, s>>>((int)nrows, (int)ncols, four, avg_res, d_g, node, nullptr, off.p, cb, k0.p, v0.p);
+  rc = sort_pairs(s, k0.p, k1.p, v0.p, v1.p, m, 2 * cb, err);
+  if (!rc) {
+    k0.release();
+    v0.release();
+    bool over = false;
+    rc = compress_to_csr(s, m, k1.p, v1.p, nnode, nnode, cb, false, 0, 0, &over, out, err);
+  }
+  if (rc) { cudaFree(node); free_csr(out); return rc; }
+  CKD(cudaStreamSynchronize(s));
+  *d_nodemap = node;
   return 0;
 }
 

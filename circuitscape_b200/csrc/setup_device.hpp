@@ -112,6 +112,16 @@ template <typename T>
 int build_dia(cudaStream_t stream, const int* d_rowptr, const int* d_colidx, const T* d_vals, int64_t n, T** d_dia,
               int* nr, size_t* ld, std::string& err);
 
+// Raster -> Laplacian WITH short-circuit polygons on the device (src/raster/pairwise.jl:271-367 +
+// src/core.jl:608-624): every cell of a polygon (NODATA cells too) takes the node of the polygon's first
+// valid cell, labels are compacted in order, parallel cell adjacencies of merged nodes add up, adjacencies
+// inside a node are dropped.  d_g: conductances (fp64, column-major cells; <= 0 / NaN = not a node of its
+// own, and 0 for the averaging rules); d_poly: polygon id per cell (0 = none, ids <= max_poly) or null.
+// out: CSR (fp64, cudaMalloc'ed); *d_nodemap: node id per cell (1-based, 0 = none; cudaMalloc'ed).
+int assemble_raster_polygons(cudaStream_t stream, int64_t nrows, int64_t ncols, const double* d_g, const int* d_poly,
+                             int max_poly, int four_neighbors, int avg_res, DCsr& out, int** d_nodemap,
+                             std::string& err);
+
 // narrow caller indices (int32 / int64, base 0 / 1) to int32 0-based on the device
 int narrow_indices(cudaStream_t stream, const void* d_src, int index_bits, int index_base, int64_t count, int* d_dst);
 int convert_values(cudaStream_t stream, const double* d_in, float* d_out, int64_t count);

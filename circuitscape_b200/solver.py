@@ -113,6 +113,33 @@ class B200Factor:
         return opts
 
     @classmethod
+    def from_raster_polygons(cls, conductance, polymap, solver: "CUDASolver", four_neighbors=False, avg_res=False,
+                             log_transform=False):
+        """Factor of a raster WITH short-circuit polygons, assembled on the device
+        (cs_b200_create_from_raster_poly: construct_node_map with a polygon map, construct_graph with
+        summed parallel adjacencies, laplacian!).  Returns (factor, nodemap) -- nodemap as the reference's
+        (1-based node id per cell, 0 = none).  NODATA cells may be given as 0 or negative values."""
+        lib = _lib.load()
+        f = cls.__new__(cls)
+        f._lib = lib
+        f._h = C.c_void_p()
+        f.io_dtype = np.dtype(solver.dtype)
+        f.dtype = np.dtype(solver.device_dtype)
+        f.solver = solver
+        g = np.asfortranarray(conductance, dtype=f.dtype)
+        pm = None if polymap is None else np.asfortranarray(polymap, dtype=np.int32)
+        nodemap = np.zeros(g.shape, dtype=np.int32, order="F")
+        n, nnz = C.c_int64(), C.c_int64()
+        opts = cls._opts(solver, log_transform)
+        rc = lib.cs_b200_create_from_raster_poly(g.shape[0], g.shape[1], _lib._ptr(g), _lib._ptr(pm),
+                                                 _lib.dtype_code(f.dtype), 1 if four_neighbors else 0,
+                                                 1 if avg_res else 0, solver.device, C.byref(opts), C.byref(f._h),
+                                                 C.byref(n), C.byref(nnz), _lib._ptr(nodemap))
+        _lib.check(lib, None, rc)
+        f.n = n.value
+        return f, nodemap
+
+    @classmethod
     def from_raster(cls, conductance, solver: "CUDASolver", four_neighbors=False, avg_res=False,
                     log_transform=False):
         """Factor of a whole conductance raster, assembled ON THE DEVICE

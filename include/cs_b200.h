@@ -126,6 +126,18 @@ int cs_b200_create_from_raster(int64_t nrows, int64_t ncols, const void* g, int 
                                const cs_b200_opts* opts, cs_b200_handle** out,
                                int64_t* n_out, int64_t* nnz_out);
 
+/* Same with SHORT-CIRCUIT POLYGONS (construct_node_map with a polygon map, src/raster/pairwise.jl:283-314):
+ * polymap: host, column-major nrows x ncols int32, 0 = no polygon (NULL = none).  Every cell of a polygon,
+ * NODATA cells included, takes the node of the polygon's first valid cell; node labels are compacted in
+ * order; parallel cell adjacencies between merged nodes add up and adjacencies inside a node vanish
+ * (sparse(I,J,V) + laplacian!, src/core.jl:608-624).  nodemap_out (optional): host, column-major
+ * nrows x ncols int32, the node id of every cell (1-based like the reference's nodemap, 0 = none) --
+ * what the host needs to place focal points, sources and grounds.                                   */
+int cs_b200_create_from_raster_poly(int64_t nrows, int64_t ncols, const void* g, const int32_t* polymap,
+                                    int dtype, int four_neighbors, int avg_res, int device,
+                                    const cs_b200_opts* opts, cs_b200_handle** out, int64_t* n_out,
+                                    int64_t* nnz_out, int32_t* nodemap_out);
+
 /* Copy the handle's CSR (0-based, int32 indices, values of the handle's dtype) to host buffers
  * of n+1, nnz and nnz elements; any pointer may be NULL.  Parity / debugging hook.            */
 int cs_b200_get_csr(cs_b200_handle* h, int32_t* rowptr, int32_t* colidx, void* vals);

@@ -158,3 +158,59 @@ def test_solve_on_device_assembled_raster(precond):
         c1, m1 = f1.read_currents()
     assert np.abs(r1["R"] - r0["R"]).max() <= 1e-9 * np.abs(r0["R"]).max()
     assert np.abs(c1 - c0).max() <= 1e-6 * np.abs(c0).max()
+
+
+# ---- short-circuit polygons on the device (round 2) ------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("four,avg_res", [(False, False), (True, True), (False, True)])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_device_assembly_with_polygons_matches_host(seed, four, avg_res):
+    """construct_node_map + construct_graph + laplacian! with a polygon map (src/raster/pairwise.jl:283-314):
+    polygons over NODATA cells, a polygon without any valid cell, touching polygons, merged parallel
+    adjacencies -- node map and Laplacian against the host assembly (circuitscape_b200/graph.py)."""
+    import circuitscape_b200 as cb
+    from circuitscape_b200 import graph
+    rng = np.random.default_rng(seed)
+    nr, nc = 41 + 7 * seed, 37
+    g = rng.uniform(0.1, 1.0, size=(nr, nc))
+    g[rng.random(g.shape) < 0.15] = 0.0                       # NODATA
+    poly = np.zeros((nr, nc), dtype=np.int64)
+    poly[3:9, 4:11] = 1
+    poly[9:12, 4:8] = 2                                       # touches polygon 1
+    poly[20:23, 20:30] = 7
+    poly[30:33, 1:4] = 5
+    g[30:33, 1:4] = 0.0                                       # polygon 5 has no valid cell at all
+    poly[rng.integers(0, nr, 25), rng.integers(0, nc, 25)] = 9   # scattered cells of one polygon
+    nm_host = graph.construct_node_map(g, poly)
+    L_host = graph.laplacian(graph.construct_graph(g, nm_host, avg_res, four)).tocsr()
+    f, nm_dev = cb.B200Factor.from_raster_polygons(g, poly, cb.CUDASolver(precond="jacobi"), four_neighbors=four,
+                                                   avg_res=avg_res)
+    with f:
+        L_dev = f.get_csr()
+    assert np.array_equal(nm_dev, nm_host)
+    assert L_dev.shape == L_host.shape
+    d = (L_dev - L_host).tocsr()
+    assert abs(d).max() <= 1e-13 * abs(L_host).max()
+    assert np.abs(np.asarray(L_dev.sum(axis=1))).max() <= 1e-12     # a Laplacian: zero row sums
+
+
+@pytest.mark.gpu
+def test_device_assembly_with_polygons_solves_like_the_host_path():
+    import circuitscape_b200 as cb
+    from circuitscape_b200 import graph
+    rng = np.random.default_rng(3)
+    g = rng.uniform(0.1, 1.0, size=(150, 140))
+    g[rng.random(g.shape) < 0.05] = 0.0
+    poly = np.zeros(g.shape, dtype=np.int64)
+    poly[10:30, 10:25] = 3
+    poly[100:140, 60:70] = 4
+    nm = graph.construct_node_map(g, poly)
+    L = graph.laplacian(graph.construct_graph(g, nm, False, False))
+    comp = max(graph.connected_components(L), key=len)
+    a, b = int(comp[5]) - 1, int(comp[-7]) - 1
+    with cb.B200Factor(L, cb.CUDASolver(rtol=1e-9)) as f0:
+        R0 = f0.solve_pairs([a], [b])["R"][0]
+    f, nm_dev = cb.B200Factor.from_raster_polygons(g, poly, cb.CUDASolver(rtol=1e-9))
+    with f:
+        R1 = f.solve_pairs([a], [b])["R"][0]
+    assert np.array_equal(nm_dev, nm) and abs(R0 - R1) <= 1e-7 * R0
