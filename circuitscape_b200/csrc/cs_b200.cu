@@ -877,6 +877,42 @@ int ew_grid_n(cs_b200_handle* h, int64_t n_pad) {
   return (int)std::max<size_t>(1, std::min<size_t>(h->grid_ew, (nelem + per - 1) / per));
 }
 
+// fused upward step of a stencil-form level (kernels.cuh k_stencil_prolong_jacobi):
+//   Yout = (X0 + P Yc) + omega D^-1 (B - A (X0 + P Yc))   [+ dot(B, Yout) on the finest level]
+template <typename T, int KT, int MODE>
+void launch_prolong_jacobi(cs_b200_handle* h, DevLevel& L, const T* Yc, const T* X0, T* Yout, const T* B, bool timed) {
+  const DevCsr& m = L.A;
+  const DiaDev<T> a{(const T*)m.dia, m.dia_ld, m.nrows, m.dia_nr};
+  const CsrP<T> p{L.P.rowptr, L.P.colidx, (const T*)L.P.vals};
+  const SpmmEpi<T> ep{B, (const T*)L.dinv, (T)L.omega, h->d_ctl, h->d_partials};
+  constexpr int V16 = 16 / (int)sizeof(T);
+  constexpr int CGn = KT / (KT < V16 ? KT : V16);
+  constexpr int RPP = NT / CGn;
+  constexpr int SMEM = (RPP + 2) * (PJ_TC + 2) * KT * (int)sizeof(T);
+  static_assert(SMEM <= 48 * 1024, "tile fits the default dynamic shared memory");
+  const long long ntiles = (long long)((m.dia_nr + RPP - 1) / RPP) *
+                           ((((long long)m.nrows + m.dia_nr - 1) / m.dia_nr + PJ_TC - 1) / PJ_TC);
+  const int grid = (int)std::max<long long>(1, std::min<long long>(h->grid_spmm, ntiles));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool prof = h->profile && timed;
+  if (prof) {
+    if (h->prof_used + 2 > h->prof_ev.size())
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_ev.push_back(e); }
+    e0 = h->prof_ev[h->prof_used++];
+    e1 = h->prof_ev[h->prof_used++];
+    // the two launches it replaces: SP_ADD on P (nnz_P (s+4) + (n+1) 4 + Yc + X read + X write) and the
+    // Jacobi sweep on A (nnz (s+4) + (n+1) 4 + X + Y + B + 1/diag)
+    h->prof_bytes += (double)m.nnz * (sizeof(T) + 4) + (double)(m.nrows + 1) * 4 + 3.0 * (double)m.nrows * KT * sizeof(T) +
+                     (double)m.nrows * sizeof(T) + (double)L.P.nnz * (sizeof(T) + 4) + (double)(m.nrows + 1) * 4 +
+                     2.0 * (double)m.nrows * KT * sizeof(T);
+    cudaEventRecord(e0, h->stream);
+  }
+  k_stencil_prolong_jacobi<T, KT, MODE><<<grid, NT, SMEM, h->stream>>>(a, p, Yc, X0, Yout, ep);
+  if (prof) cudaEventRecord(e1, h->stream);
+  h->stats.kernel_launches++;
+  if (timed) h->stats.spmm_launches++;
+}
+
 // z = M^-1 r : one V(1,1) cycle, damped Jacobi, on panels of width KT.
 //   in : h->R (residual, read-only)      out: h->Z ; rho_new = r.z folded into the last kernel
 // Level buffers: b = right-hand side, x = running correction, t = residual scratch,
@@ -916,8 +952,15 @@ void launch_vcycle_on(cs_b200_handle* h, std::vector<DevLevel>& lv, const VcBufs
       launch_spmm_on<T, KT, SP_JACOBI>(h, C.A, X(l), Y(l), B(l), (const T*)C.dinv, C.omega, false);
     }
   }
+  static const bool fuse_off = std::getenv("CS_B200_NO_FUSED_PROLONG") != nullptr;
   for (int l = nl - 2; l >= 0; --l) {
     DevLevel& L = lv[l];
+    if (L.A.dia && !fuse_off) {
+      // stencil-form level: prolongate + correct + post-smooth in one kernel (x1 stays in shared memory)
+      if (l == 0) launch_prolong_jacobi<T, KT, SP_JACOBI_DOT>(h, L, Y(l + 1), X(l), Y(l), B(l), true);
+      else launch_prolong_jacobi<T, KT, SP_JACOBI>(h, L, Y(l + 1), X(l), Y(l), B(l), false);
+      continue;
+    }
     launch_spmm_on<T, KT, SP_ADD>(h, L.P, Y(l + 1), X(l), X(l) /* staged as B */, nullptr, 0.0, false);
     if (l == 0)
       launch_spmm_on<T, KT, SP_JACOBI_DOT>(h, L.A, X(l), Y(l), B(l), (const T*)L.dinv, L.omega, true);
@@ -1139,6 +1182,26 @@ int gather_panel_status(cs_b200_handle* h, int kt, int64_t c0, int64_t* iters, d
   return 0;
 }
 
+// node currents of the panel in X (src/out.jl:178-290): branch-current maxima, then max(inflow, outflow)
+// per node with the 1e-8 zeroing, accumulated into the cumulative / max vectors (src/out.jl:100-107)
+template <typename T, int KT>
+void launch_currents(cs_b200_handle* h, bool want_curr, int accumulate) {
+  const int grid = (int)std::min<int64_t>(h->grid_spmm, (h->n + (NT / KT) - 1) / (NT / KT));
+  if (h->A0.dia) {
+    const DiaDev<T> a{(const T*)h->A0.dia, h->A0.dia_ld, (int)h->n, h->A0.dia_nr};
+    k_cur_max_dia<T, KT><<<grid, NT, 0, h->stream>>>(a, (const T*)h->X, h->d_ctl, h->d_partials);
+    k_cur_acc_dia<T, KT><<<grid, NT, 0, h->stream>>>(a, (const T*)h->X, h->d_ctl, want_curr ? (T*)h->AP : nullptr,
+                                                     (T*)h->d_cum, (T*)h->d_max, accumulate, h->opts.log_transform, KT);
+  } else {
+    k_cur_max<T, KT><<<grid, NT, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx, (const T*)h->d_vals,
+                                                 (const T*)h->X, h->d_ctl, h->d_partials);
+    k_cur_acc<T, KT><<<grid, NT, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx, (const T*)h->d_vals,
+                                                 (const T*)h->X, h->d_ctl, want_curr ? (T*)h->AP : nullptr,
+                                                 (T*)h->d_cum, (T*)h->d_max, accumulate, h->opts.log_transform, KT);
+  }
+  h->stats.kernel_launches += 2;
+}
+
 int next_kt(int64_t remaining, int ktmax) {
   int kt = ktmax;
   while (kt > remaining) kt >>= 1;
@@ -1168,15 +1231,7 @@ int pairs_panel(cs_b200_handle* h, int64_t c0, const int64_t* src, const int64_t
   k_pair_extract<T, KT><<<1, 32, 0, h->stream>>>((const T*)h->X, h->d_ctl);
   h->stats.kernel_launches++;
   if (accumulate || curr) {
-    const int grid = (int)std::min<int64_t>(h->grid_spmm, (h->n + (NT / KT) - 1) / (NT / KT));
-    k_cur_max<T, KT><<<grid, NT, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx,
-                                                 (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
-                                                 h->d_partials);
-    k_cur_acc<T, KT><<<grid, NT, 0, h->stream>>>(
-        (int)h->n, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
-        curr ? (T*)h->AP : nullptr, (T*)h->d_cum, (T*)h->d_max, accumulate,
-        h->opts.log_transform, KT);
-    h->stats.kernel_launches += 2;
+    launch_currents<T, KT>(h, curr != nullptr, accumulate);
   }
   CK(h, cudaGetLastError());
   const int tg = (int)std::min<size_t>(4096, (nelem + 255) / 256);
@@ -1257,15 +1312,7 @@ int sources_panel(cs_b200_handle* h, int64_t c0, const int64_t* colptr, const in
     h->stats.d2h_bytes += (double)nprobe * KT * sizeof(T);
   }
   if (accumulate || curr) {
-    const int grid = (int)std::min<int64_t>(h->grid_spmm, (h->n + (NT / KT) - 1) / (NT / KT));
-    k_cur_max<T, KT><<<grid, NT, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx,
-                                                 (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
-                                                 h->d_partials);
-    k_cur_acc<T, KT><<<grid, NT, 0, h->stream>>>(
-        (int)h->n, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
-        curr ? (T*)h->AP : nullptr, (T*)h->d_cum, (T*)h->d_max, accumulate,
-        h->opts.log_transform, KT);
-    h->stats.kernel_launches += 2;
+    launch_currents<T, KT>(h, curr != nullptr, accumulate);
   }
   CK(h, cudaGetLastError());
   const int tg = (int)std::min<size_t>(4096, (nelem + 255) / 256);
@@ -1364,15 +1411,7 @@ int combine_panel(cs_b200_handle* h, int64_t c0, const int64_t* nodes, const int
   k_pair_extract<T, KT><<<1, 32, 0, h->stream>>>((const T*)h->X, h->d_ctl);
   h->stats.kernel_launches++;
   if (accumulate || curr) {
-    const int grid = (int)std::min<int64_t>(h->grid_spmm, (h->n + (NT / KT) - 1) / (NT / KT));
-    k_cur_max<T, KT><<<grid, NT, 0, h->stream>>>((int)h->n, h->d_rowptr, h->d_colidx,
-                                                 (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
-                                                 h->d_partials);
-    k_cur_acc<T, KT><<<grid, NT, 0, h->stream>>>(
-        (int)h->n, h->d_rowptr, h->d_colidx, (const T*)h->d_vals, (const T*)h->X, h->d_ctl,
-        curr ? (T*)h->AP : nullptr, (T*)h->d_cum, (T*)h->d_max, accumulate,
-        h->opts.log_transform, KT);
-    h->stats.kernel_launches += 2;
+    launch_currents<T, KT>(h, curr != nullptr, accumulate);
   }
   CK(h, cudaGetLastError());
   if (curr) {

@@ -1052,6 +1052,157 @@ k_stencil(const DiaDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const S
   }
 }
 
+// ---------------------------------------------------------------------------
+// Upward leg of the V-cycle on a stencil-form level, fused:  prolongate + correct + post-smooth
+//     x1 = x0 + P y          (y: the coarser level's correction, P: plain CSR, ~3 entries per row)
+//     z  = x1 + omega D^-1 (b - A x1)        [+ dot(b, z) -> CG beta / stop test on the finest level]
+// One CTA owns a tile of RPP rows x PJ_TC raster columns; it first builds x1 for the tile AND its one-cell
+// halo in shared memory (the halo's P rows are recomputed: 27 % more P / x0 traffic at 128 x 8), then applies
+// the 9 diagonals out of shared memory.  x1 never goes to global memory: against the two-kernel form
+// (k_spmm_win SP_ADD then k_stencil SP_JACOBI_DOT) that saves the write and both re-reads of the x panel
+// and the per-block overhead of the windowed kernel on the 3-entry rows of P.
+// ---------------------------------------------------------------------------
+constexpr int PJ_TC = 8;
+
+template <typename T> struct CsrP {
+  const int* rowptr;
+  const int* colidx;
+  const T* vals;
+};
+
+template <typename T, int KT, int MODE>
+__global__ void __launch_bounds__(NT)
+k_stencil_prolong_jacobi(const DiaDev<T> A, const CsrP<T> P, const T* __restrict__ Yc, const T* __restrict__ X0,
+                         T* __restrict__ Z, const SpmmEpi<T> ep) {
+  static_assert(MODE == SP_JACOBI || MODE == SP_JACOBI_DOT, "post-smoothing modes only");
+  constexpr int V16 = 16 / (int)sizeof(T);
+  constexpr int CPT = KT < V16 ? KT : V16;
+  constexpr int CG = KT / CPT;
+  constexpr int RPP = NT / CG;
+  constexpr int RH = RPP + 2, CH = PJ_TC + 2;
+  extern __shared__ __align__(16) unsigned char pj_smem[];
+  T* xs = reinterpret_cast<T*>(pj_smem);                 // [CH][RH][KT]
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, rl = tid / CG, c0 = cg * CPT;
+  const int n = A.n, nr = A.nr;
+  const int ncol = (n + nr - 1) / nr;
+  const int nrc = (nr + RPP - 1) / RPP;
+  const int ntc = (ncol + PJ_TC - 1) / PJ_TC;
+  const long long ntiles = (long long)nrc * ntc;
+  double dot0[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) dot0[i] = 0.0;
+
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tc = (int)(t / nrc), rc = (int)(t % nrc);
+    __syncthreads();                                     // the previous tile's readers are done
+    // ---- phase 1: x1 = x0 + P y on the tile and its halo
+    for (int it = tid; it < RH * CH * CG; it += NT) {
+      const int g = it % CG;
+      const int rr = (it / CG) % RH;
+      const int cc = it / (CG * RH);
+      const int c = tc * PJ_TC + cc - 1, r = rc * RPP + rr - 1;
+      T x1[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) x1[i] = T(0);
+      const long long row_l = (long long)c * nr + r;
+      if (c >= 0 && c < ncol && r >= 0 && r < nr && row_l < n) {
+        const int row = (int)row_l;
+        const int a = P.rowptr[row], b = P.rowptr[row + 1];
+        ldvec<T, CPT>(X0 + (size_t)row * KT + g * CPT, x1);
+        // a prolongator row has <= 4 entries on a regular grid (the aggregates its 3 x 3 neighbourhood
+        // touches): columns and values of the first four go out together, then the four gathers
+        int cj[4];
+        T pv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool ok = a + q < b;
+          cj[q] = ok ? __ldg(P.colidx + a + q) : 0;
+          pv[q] = ok ? __ldg(P.vals + a + q) : T(0);
+        }
+        T yv[4][CPT];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ldvec<T, CPT>(Yc + (size_t)cj[q] * KT + g * CPT, yv[q]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) x1[i] += pv[q] * yv[q][i];
+        for (int j = a + 4; j < b; ++j) {
+          const T pw = P.vals[j];
+          T yw[CPT];
+          ldvec<T, CPT>(Yc + (size_t)P.colidx[j] * KT + g * CPT, yw);
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) x1[i] += pw * yw[i];
+        }
+      }
+      stvec<T, CPT>(xs + ((size_t)cc * RH + rr) * KT + g * CPT, x1);
+    }
+    __syncthreads();
+    // ---- phase 2: z = x1 + omega D^-1 (b - A x1)
+    const int r = rc * RPP + rl;
+    if (r < nr) {
+      const int cbeg = tc * PJ_TC;
+      int cend = min(ncol, (tc + 1) * PJ_TC);
+      if ((long long)(cend - 1) * nr + r >= n) cend = (int)((n - 1 - r) / nr) + 1;      // ragged last column
+      // the global operands of column c + 1 (9 diagonals, b, 1/diag) are requested before column c is
+      // combined out of shared memory
+      T v[9], bb[CPT], dv = T(0);
+      auto fetch = [&](int c, T (&vv)[9], T (&bv)[CPT], T& d) {
+        const int row = c * nr + r;
+#pragma unroll
+        for (int s = 0; s < 9; ++s) vv[s] = __ldcs(A.vals + (size_t)s * A.ld + row);
+        ldvec<T, CPT>(ep.B + (size_t)row * KT + c0, bv);
+        d = ep.omega * ep.dinv[row];
+      };
+      if (cbeg < cend) fetch(cbeg, v, bb, dv);
+      for (int c = cbeg; c < cend; ++c) {
+        const int row = c * nr + r;
+        const int cc = c - cbeg + 1, rr = rl + 1;
+        T vn[9], bn[CPT], dn = T(0);
+#pragma unroll
+        for (int s = 0; s < 9; ++s) vn[s] = T(0);
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) bn[i] = T(0);
+        if (c + 1 < cend) fetch(c + 1, vn, bn, dn);
+        T acc[CPT], xo[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) acc[i] = T(0);
+#pragma unroll
+        for (int s = 0; s < 9; ++s) {
+          T xv[CPT];
+          ldvec<T, CPT>(xs + ((size_t)(cc + s / 3 - 1) * RH + (rr + s % 3 - 1)) * KT + c0, xv);
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            acc[i] += v[s] * xv[i];
+            if (s == 4) xo[i] = xv[i];
+          }
+        }
+        T out[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const T zn = xo[i] + dv * (bb[i] - acc[i]);
+          out[i] = zn;
+          if (MODE == SP_JACOBI_DOT) dot0[i] += (double)bb[i] * (double)zn;
+        }
+        stvec<T, CPT>(Z + (size_t)row * KT + c0, out);
+#pragma unroll
+        for (int s = 0; s < 9; ++s) v[s] = vn[s];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) bb[i] = bn[i];
+        dv = dn;
+      }
+    }
+  }
+  if (MODE == SP_JACOBI_DOT) {
+    CSB_REDUCE_SMEM(1, KT)
+    double v[1][CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) v[0][i] = dot0[i];
+    if (grid_reduce<KT, CPT, 1, false>(v, ep.partials, &ep.ctl->ticket, s_warp, s_tree, s_out))
+      cg_after_precond<KT>(ep.ctl, s_out);
+  }
+}
+
 // Build the per-block records of the windowed form on the device: one CTA per block copies
 // the values (through the host-built permutation), the 16-bit local columns and the row
 // offsets into  blob + blob_off16*16 :  [ values nnzp | lcol nnzp | roff roffp ].
@@ -1510,6 +1661,102 @@ k_cur_acc(int n, const int* __restrict__ rowptr, const int* __restrict__ colidx,
     }
     if (accumulate) {
       // out.jl:305-309 (log transform) then out.jl:100-107 (cum += , max = max)
+      T val = cur;
+      if (log_transform) val = cur > T(0) ? (T)log10((double)cur) : T(-9999);
+      const unsigned mask = 0xffffffffu;
+      const int lane = threadIdx.x & 31;
+      const int base = lane - c;
+      double s = 0.0;
+      T m = T(-1.0e30);
+#pragma unroll
+      for (int cc = 0; cc < KT; ++cc) {
+        const T vv = __shfl_sync(mask, val, base + cc);
+        const double ww = __shfl_sync(mask, w, base + cc);
+        if (cc < ncols && ww != 0.0) {
+          s += ww * (double)vv;
+          m = vv > m ? vv : m;
+        }
+      }
+      if (c == 0 && row < n) {
+        cum[row] = (T)((double)cum[row] + s);
+        if (mx) mx[row] = m > mx[row] ? m : mx[row];
+      }
+    }
+  }
+}
+
+// the same two passes on the stencil (DIA) form of the operator: 9 coalesced value loads and 9 panel
+// gathers per (row, column), no CSR walk (the CSR versions run at ~1/8 of the HBM rate).  Slots
+// without a stored entry hold 0 and are skipped, so the candidates of the maxima are the stored ones.
+template <typename T, int KT>
+__global__ void __launch_bounds__(NT)
+k_cur_max_dia(const DiaDev<T> A, const T* __restrict__ V, PanelCtl* ctl, double* partials) {
+  CSB_REDUCE_SMEM(2, KT)
+  const int c = threadIdx.x % KT;
+  constexpr int RPP = NT / KT;
+  const int n = A.n, nr = A.nr;
+  double mp = -1.0e300, mn = -1.0e300;
+  for (int row = blockIdx.x * RPP + threadIdx.x / KT; row < n; row += gridDim.x * RPP) {
+    T a[4], vj[4];
+    const T vi = V[(size_t)row * KT + c];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                       // the four slots with column > row: +1, nr-1, nr, nr+1
+      const int s = 5 + q;
+      a[q] = __ldg(A.vals + (size_t)s * A.ld + row);
+      const int j = min(n - 1, row + (s / 3 - 1) * nr + (s % 3 - 1));
+      vj[q] = V[(size_t)j * KT + c];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (a[q] != T(0)) {
+        const T d = fabs(a[q]) * (vi - vj[q]);
+        mp = fmax(mp, (double)d);
+        mn = fmax(mn, (double)(-d));
+      }
+  }
+  double v[2][1] = {{mp}, {mn}};
+  if (grid_reduce<KT, 1, 2, true>(v, partials, &ctl->ticket, s_warp, s_tree, s_out)) {
+    if (threadIdx.x < KT) {
+      ctl->maxpos[threadIdx.x] = s_out[threadIdx.x];
+      ctl->maxneg[threadIdx.x] = s_out[KT + threadIdx.x];
+    }
+  }
+}
+
+template <typename T, int KT>
+__global__ void __launch_bounds__(NT)
+k_cur_acc_dia(const DiaDev<T> A, const T* __restrict__ V, const PanelCtl* ctl, T* __restrict__ cur_out,
+              T* __restrict__ cum, T* __restrict__ mx, int accumulate, int log_transform, int ncols) {
+  const int c = threadIdx.x % KT;
+  constexpr int RPP = NT / KT;
+  const int n = A.n, nr = A.nr;
+  const T maxpos = (T)ctl->maxpos[c], maxneg = (T)ctl->maxneg[c];
+  const double w = ctl->weight[c];
+  const int nrow_iter = (n + RPP - 1) / RPP;
+  for (int it = blockIdx.x; it < nrow_iter; it += gridDim.x) {
+    const int row = it * RPP + threadIdx.x / KT;
+    T cur = T(0);
+    if (row < n) {
+      T a[9], vj[9];
+#pragma unroll
+      for (int s = 0; s < 9; ++s) {
+        a[s] = __ldg(A.vals + (size_t)s * A.ld + row);
+        const int j = max(0, min(n - 1, row + (s / 3 - 1) * nr + (s % 3 - 1)));
+        vj[s] = V[(size_t)j * KT + c];
+      }
+      const T vi = vj[4];
+      T inflow = T(0), outflow = T(0);
+#pragma unroll
+      for (int s = 0; s < 9; ++s) {
+        if (s == 4) continue;
+        const T d = fabs(a[s]) * (vi - vj[s]);
+        if (!(fabs(d / maxneg) < T(1e-8)) && d > T(0)) outflow += d;
+        if (!(fabs(d / maxpos) < T(1e-8)) && d < T(0)) inflow -= d;
+      }
+      cur = inflow > outflow ? inflow : outflow;
+      if (cur_out) cur_out[(size_t)row * KT + c] = cur;
+    }
+    if (accumulate) {
       T val = cur;
       if (log_transform) val = cur > T(0) ? (T)log10((double)cur) : T(-9999);
       const unsigned mask = 0xffffffffu;
