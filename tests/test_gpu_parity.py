@@ -521,7 +521,9 @@ def test_set_grounds_matches_scipy_on_the_modified_system():
             ref[keep] = spla.splu(M[keep][:, keep].tocsc()).solve(b[keep])
             assert relres.max() < 1e-4 and iters.max() < 200
             assert np.abs(x - ref).max() <= 1e-7 * np.abs(ref).max(), trial
-            assert np.all(x[mask] == 0.0)
+            # the identity rows are solved like any other row: 0 V to solver tolerance (the host driver
+            # writes exact zeros there, as the reference re-inserts them, src/raster/advanced.jl:301-304)
+            assert np.abs(x[mask]).max() <= 1e-7 * np.abs(ref).max()
         f.set_grounds(None, None)                        # pristine singular operator again
         nodes = graph.focal_nodes(n, 3, seed=7)
         src, dst = graph.all_pairs(nodes)
