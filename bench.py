@@ -480,6 +480,7 @@ def main():
         factor.reset_currents()
         factor.solve_pairs(msrc[:kk], mdst[:kk], accumulate=True)
         pbytes = factor.profile_bytes()
+        pclasses = factor.profile_classes()
         pms, pl = factor.profile_spmm(False)
         avg_bytes = pbytes / max(pl, 1)
         achieved = pbytes / (pms * 1e-3) / 1e9
@@ -487,7 +488,7 @@ def main():
         tnote = "no ncu --set full capture for this size"
         tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tpath):
-            tj = json.load(open(tpath)).get(f"finest_level_spmm_{args.rows}x{args.cols}")
+            tj = json.load(open(tpath)).get(f"finest_level_{args.rows}x{args.cols}")
             if tj:
                 traffic = tj.get("traffic_bytes_per_launch")
                 tnote = tj.get("note", "")
@@ -504,6 +505,8 @@ def main():
                 "traffic": traffic, "traffic_note": tnote, "peak_source": peak_src, "launches": int(pl),
                 "avg_launch_ms": pms / max(pl, 1), "algorithmic_bytes_per_launch": avg_bytes,
                 "spmm_share_of_step": pms / max(t_full, 1e-9),
+                "by_kernel": {k: {"launches": c, "avg_ms": m / c, "GB/s": b / (m * 1e-3) / 1e9, "frac": b / (m * 1e-3) / 1e9 / peak}
+                              for k, (m, b, c) in pclasses.items()},
                 "note": "per-launch CUDA events on the solve stream in an instrumented repeat of the first "
                         f"{kk} pairs of the step (plain launches, same kernels as the graph); bytes = "
                         "nnz(s_v+4)+(n+1)4+panel passes summed per launch by the library (DESIGN.md section 4); "

@@ -58,6 +58,10 @@ struct DevCsr {
   void* dia = nullptr;
   size_t dia_ld = 0;
   int dia_nr = 0;
+  // ELL-4 copy of a prolongator with <= 4 entries per row (k_stencil_prolong_jacobi); null otherwise
+  int* ell_col = nullptr;
+  void* ell_val = nullptr;
+  size_t ell_ld = 0;
 };
 
 // one multigrid level below the finest (the finest level aliases the handle's own CSR)
@@ -130,6 +134,11 @@ struct cs_b200_handle {
   double prof_ms = 0.0;
   double prof_bytes = 0.0;   // algorithmic bytes of the timed launches (DESIGN.md §4 formula)
   int64_t prof_launches = 0;
+  // the same per kernel class: slot = 2 * MODE + (fp32 ? 1 : 0), MODE 7 = fused prolongation + sweep
+  std::vector<int> prof_slot;           // one entry per event pair in flight
+  std::vector<double> prof_pair_bytes;
+  double prof_slot_ms[16] = {}, prof_slot_bytes[16] = {};
+  int64_t prof_slot_launches[16] = {};
   std::string err;
   size_t esize() const { return dtype == CS_B200_F64 ? 8 : 4; }
 };
@@ -236,8 +245,8 @@ int upload_csr(cs_b200_handle* h, const csb_amg::Csr& m, DevCsr& d, bool windowe
 }
 
 void free_win(DevCsr& d) {
-  cudaFree(d.win_meta); cudaFree(d.blob); cudaFree(d.dia);
-  d.win_meta = nullptr; d.blob = nullptr; d.dia = nullptr;
+  cudaFree(d.win_meta); cudaFree(d.blob); cudaFree(d.dia); cudaFree(d.ell_col); cudaFree(d.ell_val);
+  d.win_meta = nullptr; d.blob = nullptr; d.dia = nullptr; d.ell_col = nullptr; d.ell_val = nullptr;
 }
 
 void free_csr(DevCsr& d) {
@@ -603,6 +612,14 @@ int adopt_levels(cs_b200_handle* h, csb_dev::DHierarchy& hier, std::vector<DevLe
     if (l + 1 < nl) {
       int rc = adopt_csr<TV>(h, hl.P, false, L.P, L.n >= 20000 && (win_mask() & 4), (const TV*)nullptr);
       if (rc) return rc;
+      if (L.A.dia) {          // the fused prolongation kernel of this level reads P as ELL-4 when it can
+        int* ec = nullptr;
+        TV* ev = nullptr;
+        size_t eld = 0;
+        int rce = csb_dev::build_ell4<TV>(h->stream, L.P.rowptr, L.P.colidx, (const TV*)L.P.vals, L.P.nrows, &ec, &ev, &eld, h->err);
+        if (rce) return rc_dev(h, rce);
+        L.P.ell_col = ec; L.P.ell_val = ev; L.P.ell_ld = eld;
+      }
       mark(l, "P");
       rc = adopt_csr<TV>(h, hl.R, false, L.R, L.n >= 20000 && (win_mask() & 8), (const TV*)nullptr);
       if (rc) return rc;
@@ -803,6 +820,8 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
       bytes += (double)m.nrows * KT * sizeof(T);
     if (MODE == SP_JACOBI || MODE == SP_JACOBI_DOT) bytes += (double)m.nrows * sizeof(T);
     h->prof_bytes += bytes;
+    h->prof_slot.push_back(2 * MODE + (sizeof(T) == 4 ? 1 : 0));
+    h->prof_pair_bytes.push_back(bytes);
     cudaEventRecord(e0, h->stream);
   }
   const SpmmEpi<T> ep{B, dinv, (T)omega, h->d_ctl, h->d_partials};
@@ -858,9 +877,17 @@ void harvest_profile(cs_b200_handle* h) {
     if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) {
       h->prof_ms += ms;
       h->prof_launches++;
+      if (i / 2 < h->prof_slot.size()) {
+        const int sl = h->prof_slot[i / 2] & 15;
+        h->prof_slot_ms[sl] += ms;
+        h->prof_slot_bytes[sl] += h->prof_pair_bytes[i / 2];
+        h->prof_slot_launches[sl]++;
+      }
     }
   }
   h->prof_used = 0;
+  h->prof_slot.clear();
+  h->prof_pair_bytes.clear();
 }
 
 template <typename T, int KT>
@@ -883,7 +910,7 @@ template <typename T, int KT, int MODE>
 void launch_prolong_jacobi(cs_b200_handle* h, DevLevel& L, const T* Yc, const T* X0, T* Yout, const T* B, bool timed) {
   const DevCsr& m = L.A;
   const DiaDev<T> a{(const T*)m.dia, m.dia_ld, m.nrows, m.dia_nr};
-  const CsrP<T> p{L.P.rowptr, L.P.colidx, (const T*)L.P.vals};
+  const CsrP<T> p{L.P.rowptr, L.P.colidx, (const T*)L.P.vals, L.P.ell_col, (const T*)L.P.ell_val, L.P.ell_ld};
   const SpmmEpi<T> ep{B, (const T*)L.dinv, (T)L.omega, h->d_ctl, h->d_partials};
   constexpr int V16 = 16 / (int)sizeof(T);
   constexpr int CGn = KT / (KT < V16 ? KT : V16);
@@ -902,9 +929,12 @@ void launch_prolong_jacobi(cs_b200_handle* h, DevLevel& L, const T* Yc, const T*
     e1 = h->prof_ev[h->prof_used++];
     // the two launches it replaces: SP_ADD on P (nnz_P (s+4) + (n+1) 4 + Yc + X read + X write) and the
     // Jacobi sweep on A (nnz (s+4) + (n+1) 4 + X + Y + B + 1/diag)
-    h->prof_bytes += (double)m.nnz * (sizeof(T) + 4) + (double)(m.nrows + 1) * 4 + 3.0 * (double)m.nrows * KT * sizeof(T) +
-                     (double)m.nrows * sizeof(T) + (double)L.P.nnz * (sizeof(T) + 4) + (double)(m.nrows + 1) * 4 +
-                     2.0 * (double)m.nrows * KT * sizeof(T);
+    const double fb = (double)m.nnz * (sizeof(T) + 4) + (double)(m.nrows + 1) * 4 + 3.0 * (double)m.nrows * KT * sizeof(T) +
+                      (double)m.nrows * sizeof(T) + (double)L.P.nnz * (sizeof(T) + 4) + (double)(m.nrows + 1) * 4 +
+                      2.0 * (double)m.nrows * KT * sizeof(T);
+    h->prof_bytes += fb;
+    h->prof_slot.push_back(2 * 7 + (sizeof(T) == 4 ? 1 : 0));
+    h->prof_pair_bytes.push_back(fb);
     cudaEventRecord(e0, h->stream);
   }
   k_stencil_prolong_jacobi<T, KT, MODE><<<grid, NT, SMEM, h->stream>>>(a, p, Yc, X0, Yout, ep);
@@ -2277,6 +2307,19 @@ int cs_b200_profile_spmm(cs_b200_handle* h, int enable, double* total_ms, int64_
     h->prof_launches = 0;
     h->prof_used = 0;
     h->prof_bytes = 0.0;
+    h->prof_slot.clear();
+    h->prof_pair_bytes.clear();
+    for (int i = 0; i < 16; ++i) { h->prof_slot_ms[i] = 0.0; h->prof_slot_bytes[i] = 0.0; h->prof_slot_launches[i] = 0; }
+  }
+  return CS_B200_OK;
+}
+
+int cs_b200_profile_classes(cs_b200_handle* h, double* ms16, double* bytes16, int64_t* launches16) {
+  if (!h) return CS_B200_ERR_ARG;
+  for (int i = 0; i < 16; ++i) {
+    if (ms16) ms16[i] = h->prof_slot_ms[i];
+    if (bytes16) bytes16[i] = h->prof_slot_bytes[i];
+    if (launches16) launches16[i] = h->prof_slot_launches[i];
   }
   return CS_B200_OK;
 }

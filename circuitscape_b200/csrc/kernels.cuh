@@ -1068,6 +1068,11 @@ template <typename T> struct CsrP {
   const int* rowptr;
   const int* colidx;
   const T* vals;
+  // ELL-4 copy (slot-major, ld apart; unused slots: column 0, value 0) when no row has more than 4
+  // entries -- the prolongator of a regular grid; null otherwise
+  const int* ell_col;
+  const T* ell_val;
+  size_t ell_ld;
 };
 
 template <typename T, int KT, int MODE>
@@ -1097,6 +1102,58 @@ k_stencil_prolong_jacobi(const DiaDev<T> A, const CsrP<T> P, const T* __restrict
     const int tc = (int)(t / nrc), rc = (int)(t % nrc);
     __syncthreads();                                     // the previous tile's readers are done
     // ---- phase 1: x1 = x0 + P y on the tile and its halo
+    if (P.ell_col) {
+      // ELL-4 prolongator: no row-offset indirection; two tile rows per thread and trip, so that
+      // 2 x (x0 + 4 columns + 4 values) independent loads, then 2 x 4 gathers of y, are in flight
+      constexpr int ITEMS = RH * CH * CG;
+      for (int it0 = tid; it0 < ITEMS; it0 += 2 * NT) {
+        int rowu[2], slot[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int it = it0 + u * NT;
+          const int g = it % CG;
+          const int rr = (it / CG) % RH;
+          const int cc = it / (CG * RH);
+          const int c = tc * PJ_TC + cc - 1, r = rc * RPP + rr - 1;
+          const long long row_l = (long long)c * nr + r;
+          ok[u] = it < ITEMS && c >= 0 && c < ncol && r >= 0 && r < nr && row_l < n;
+          rowu[u] = ok[u] ? (int)row_l : 0;
+          slot[u] = it < ITEMS ? (cc * RH + rr) * KT + g * CPT : -1;
+        }
+        T x1[2][CPT], pv[2][4];
+        int cj[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int g = (it0 + u * NT) % CG;
+          ldvec<T, CPT>(X0 + (size_t)rowu[u] * KT + g * CPT, x1[u]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            cj[u][q] = __ldg(P.ell_col + (size_t)q * P.ell_ld + rowu[u]);
+            pv[u][q] = __ldg(P.ell_val + (size_t)q * P.ell_ld + rowu[u]);
+          }
+        }
+        T yv[2][4][CPT];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int g = (it0 + u * NT) % CG;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ldvec<T, CPT>(Yc + (size_t)cj[u][q] * KT + g * CPT, yv[u][q]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (slot[u] < 0) continue;
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            T a = x1[u][i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a += pv[u][q] * yv[u][q][i];
+            x1[u][i] = ok[u] ? a : T(0);
+          }
+          stvec<T, CPT>(xs + slot[u], x1[u]);
+        }
+      }
+    } else
     for (int it = tid; it < RH * CH * CG; it += NT) {
       const int g = it % CG;
       const int rr = (it / CG) % RH;
@@ -1110,8 +1167,6 @@ k_stencil_prolong_jacobi(const DiaDev<T> A, const CsrP<T> P, const T* __restrict
         const int row = (int)row_l;
         const int a = P.rowptr[row], b = P.rowptr[row + 1];
         ldvec<T, CPT>(X0 + (size_t)row * KT + g * CPT, x1);
-        // a prolongator row has <= 4 entries on a regular grid (the aggregates its 3 x 3 neighbourhood
-        // touches): columns and values of the first four go out together, then the four gathers
         int cj[4];
         T pv[4];
 #pragma unroll

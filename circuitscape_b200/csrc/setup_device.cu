@@ -1315,6 +1315,59 @@ int assemble_raster_polygons(cudaStream_t s, int64_t nrows, int64_t ncols, const
   return 0;
 }
 
+namespace {
+template <typename T>
+__global__ void k_ell4_fill(int n, size_t ld, const int* __restrict__ ptr, const int* __restrict__ idx,
+                            const T* __restrict__ val, int* __restrict__ ecol, T* __restrict__ eval, int* __restrict__ bad) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int a = ptr[i], len = ptr[i + 1] - a;
+    if (len > 4) atomicOr(bad, 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool ok = q < len;
+      ecol[(size_t)q * ld + i] = ok ? idx[a + q] : 0;
+      eval[(size_t)q * ld + i] = ok ? val[a + q] : T(0);
+    }
+  }
+}
+}  // namespace
+
+template <typename T>
+int build_ell4(cudaStream_t s, const int* d_rowptr, const int* d_colidx, const T* d_vals, int64_t nrows, int** d_col,
+               T** d_val, size_t* ld, std::string& err) {
+  *d_col = nullptr;
+  *d_val = nullptr;
+  *ld = 0;
+  if (nrows <= 0) return 0;
+  const size_t l = ((size_t)nrows + 3) / 4 * 4;
+  Scratch<int> bad;
+  CKD(bad.alloc(1, s));
+  CKD(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+  int* ec = nullptr;
+  T* ev = nullptr;
+  CKD(cudaMalloc(&ec, 4 * l * sizeof(int)));
+  cudaError_t e = cudaMalloc(&ev, 4 * l * sizeof(T));
+  if (e != cudaSuccess) { cudaFree(ec); CKD(e); }
+  k_ell4_fill<T><<<grid_for(nrows), TPB, 0, s>>>((int)nrows, l, d_rowptr, d_colidx, d_vals, ec, ev, bad.p);
+  int hb = 1;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess || hb) {
+    cudaFree(ec);
+    cudaFree(ev);
+    if (e != cudaSuccess) { err = std::string("CUDA error ") + cudaGetErrorString(e) + " building the ELL prolongator"; return -2; }
+    return 0;
+  }
+  *d_col = ec;
+  *d_val = ev;
+  *ld = l;
+  return 0;
+}
+
+template int build_ell4<float>(cudaStream_t, const int*, const int*, const float*, int64_t, int**, float**, size_t*, std::string&);
+template int build_ell4<double>(cudaStream_t, const int*, const int*, const double*, int64_t, int**, double**, size_t*, std::string&);
+
 template int build_dia<float>(cudaStream_t, const int*, const int*, const float*, int64_t, float**, int*, size_t*, std::string&);
 template int build_dia<double>(cudaStream_t, const int*, const int*, const double*, int64_t, double**, int*, size_t*, std::string&);
 

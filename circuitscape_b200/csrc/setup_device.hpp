@@ -122,6 +122,13 @@ int assemble_raster_polygons(cudaStream_t stream, int64_t nrows, int64_t ncols, 
                              int max_poly, int four_neighbors, int avg_res, DCsr& out, int** d_nodemap,
                              std::string& err);
 
+// ELL-4 copy of a device CSR whose rows all have <= 4 entries (the prolongator of a regular grid):
+// *d_col / *d_val slot-major with leading dimension *ld (cudaMalloc'ed), padding (column 0, value 0);
+// both stay null if some row is longer.
+template <typename T>
+int build_ell4(cudaStream_t stream, const int* d_rowptr, const int* d_colidx, const T* d_vals, int64_t nrows,
+               int** d_col, T** d_val, size_t* ld, std::string& err);
+
 // narrow caller indices (int32 / int64, base 0 / 1) to int32 0-based on the device
 int narrow_indices(cudaStream_t stream, const void* d_src, int index_bits, int index_base, int64_t count, int* d_dst);
 int convert_values(cudaStream_t stream, const double* d_in, float* d_out, int64_t count);
