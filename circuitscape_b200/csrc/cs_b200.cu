@@ -904,6 +904,46 @@ int ew_grid_n(cs_b200_handle* h, int64_t n_pad) {
   return (int)std::max<size_t>(1, std::min<size_t>(h->grid_ew, (nelem + per - 1) / per));
 }
 
+// stencil-form levels keep the zero-guess Jacobi sweep implicit: x0 = omega D^-1 b is formed on the fly
+// by the residual kernel (SP_RES0) and by the fused upward kernel, never stored (CS_B200_NO_IMPLICIT_X0
+// switches back to the stored form for A/B runs)
+inline bool implicit_x0(const DevLevel& L) {
+  static const bool off = std::getenv("CS_B200_NO_IMPLICIT_X0") != nullptr || std::getenv("CS_B200_NO_FUSED_PROLONG") != nullptr;
+  return L.A.dia != nullptr && !off;
+}
+
+// T = B - A (omega D^-1 B) on a stencil-form level
+template <typename T, int KT>
+void launch_stencil_res0(cs_b200_handle* h, DevLevel& L, const T* B, T* Tout, bool timed) {
+  const DevCsr& m = L.A;
+  const DiaDev<T> a{(const T*)m.dia, m.dia_ld, m.nrows, m.dia_nr};
+  const SpmmEpi<T> ep{B, (const T*)L.dinv, (T)L.omega, h->d_ctl, h->d_partials};
+  constexpr int V16 = 16 / (int)sizeof(T);
+  constexpr int CGn = KT / (KT < V16 ? KT : V16);
+  const int rpp = NT / CGn;
+  const long long ntiles = (long long)((m.dia_nr + rpp - 1) / rpp) *
+                           ((((long long)m.nrows + m.dia_nr - 1) / m.dia_nr + ST_TC - 1) / ST_TC);
+  const int sg = (int)std::max<long long>(1, std::min<long long>(h->grid_spmm, ntiles));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool prof = h->profile && timed;
+  if (prof) {
+    if (h->prof_used + 2 > h->prof_ev.size())
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_ev.push_back(e); }
+    e0 = h->prof_ev[h->prof_used++];
+    e1 = h->prof_ev[h->prof_used++];
+    // what it replaces: the residual SpMM on A (X, B read, T written); the zero-guess sweep is folded in
+    const double fb = (double)m.nnz * (sizeof(T) + 4) + (double)(m.nrows + 1) * 4 + 3.0 * (double)m.nrows * KT * sizeof(T);
+    h->prof_bytes += fb;
+    h->prof_slot.push_back(2 * (int)SP_RES + (sizeof(T) == 4 ? 1 : 0));
+    h->prof_pair_bytes.push_back(fb);
+    cudaEventRecord(e0, h->stream);
+  }
+  k_stencil<T, KT, SP_RES0><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep);
+  if (prof) cudaEventRecord(e1, h->stream);
+  h->stats.kernel_launches++;
+  if (timed) h->stats.spmm_launches++;
+}
+
 // fused upward step of a stencil-form level (kernels.cuh k_stencil_prolong_jacobi):
 //   Yout = (X0 + P Yc) + omega D^-1 (B - A (X0 + P Yc))   [+ dot(B, Yout) on the finest level]
 template <typename T, int KT, int MODE>
@@ -959,12 +999,16 @@ void launch_vcycle_on(cs_b200_handle* h, std::vector<DevLevel>& lv, const VcBufs
   for (int l = 0; l < nl - 1; ++l) {
     DevLevel& L = lv[l];
     const size_t nelem = (size_t)L.n_pad * KT;
-    if (!(l == 0 && level0_presmoothed)) {
-      k_jacobi0<T, KT><<<ew_grid_n<T, KT>(h, L.n_pad), NT, 0, h->stream>>>(
-          nelem, B(l), (const T*)L.dinv, (T)L.omega, X(l));
-      h->stats.kernel_launches++;
+    if (implicit_x0(L)) {
+      launch_stencil_res0<T, KT>(h, L, B(l), Tm(l), l == 0);
+    } else {
+      if (!(l == 0 && level0_presmoothed)) {
+        k_jacobi0<T, KT><<<ew_grid_n<T, KT>(h, L.n_pad), NT, 0, h->stream>>>(
+            nelem, B(l), (const T*)L.dinv, (T)L.omega, X(l));
+        h->stats.kernel_launches++;
+      }
+      launch_spmm_on<T, KT, SP_RES>(h, L.A, X(l), Tm(l), B(l), nullptr, 0.0, l == 0);
     }
-    launch_spmm_on<T, KT, SP_RES>(h, L.A, X(l), Tm(l), B(l), nullptr, 0.0, l == 0);
     launch_spmm_on<T, KT, SP_PLAIN>(h, L.R, Tm(l), B(l + 1), nullptr, nullptr, 0.0, false);
   }
   {
@@ -987,8 +1031,9 @@ void launch_vcycle_on(cs_b200_handle* h, std::vector<DevLevel>& lv, const VcBufs
     DevLevel& L = lv[l];
     if (L.A.dia && !fuse_off) {
       // stencil-form level: prolongate + correct + post-smooth in one kernel (x1 stays in shared memory)
-      if (l == 0) launch_prolong_jacobi<T, KT, SP_JACOBI_DOT>(h, L, Y(l + 1), X(l), Y(l), B(l), true);
-      else launch_prolong_jacobi<T, KT, SP_JACOBI>(h, L, Y(l + 1), X(l), Y(l), B(l), false);
+      const T* x0 = implicit_x0(L) ? nullptr : X(l);
+      if (l == 0) launch_prolong_jacobi<T, KT, SP_JACOBI_DOT>(h, L, Y(l + 1), x0, Y(l), B(l), true);
+      else launch_prolong_jacobi<T, KT, SP_JACOBI>(h, L, Y(l + 1), x0, Y(l), B(l), false);
       continue;
     }
     launch_spmm_on<T, KT, SP_ADD>(h, L.P, Y(l + 1), X(l), X(l) /* staged as B */, nullptr, 0.0, false);
@@ -1027,14 +1072,16 @@ void launch_iteration(cs_b200_handle* h) {
     // x += alpha p together with p = z + beta p  (9 instead of 11 panel passes)
     if (h->mixed) {
       k_cg_update_r0<T, KT, float><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->AP, (const T*)h->d_dinv,
-                                                            (T)h->lv[0].omega, (T*)h->R, (float*)h->X32,
+                                                            (T)h->lv[0].omega, (T*)h->R,
+                                                            implicit_x0(h->lv32[0]) ? nullptr : (float*)h->X32,
                                                             (float*)h->R32, h->d_ctl);
       launch_vcycle<T, KT>(h, true);
       k_cg_update_xp2<T, KT, float><<<g, NT, 0, h->stream>>>(nelem, (const float*)h->Z32, (T*)h->X, (T*)h->P,
                                                              h->d_ctl);
     } else {
       k_cg_update_r0<T, KT, T><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->AP, (const T*)h->d_dinv,
-                                                        (T)h->lv[0].omega, (T*)h->R, (T*)h->stage, nullptr,
+                                                        (T)h->lv[0].omega, (T*)h->R,
+                                                        implicit_x0(h->lv[0]) ? nullptr : (T*)h->stage, nullptr,
                                                         h->d_ctl);
       launch_vcycle<T, KT>(h, true);
       k_cg_update_xp2<T, KT, T><<<g, NT, 0, h->stream>>>(nelem, (const T*)h->Z, (T*)h->X, (T*)h->P, h->d_ctl);

@@ -256,7 +256,8 @@ __device__ __forceinline__ void cg_after_precond(PanelCtl* ctl, const double* rh
 // A row longer than NNZ_CAP (polygon hub / power-law node) is its own block and is
 // reduced by the whole CTA.
 // ---------------------------------------------------------------------------
-enum { SP_PLAIN = 0, SP_CG = 1, SP_RESNORM = 2, SP_RES = 3, SP_JACOBI = 4, SP_JACOBI_DOT = 5, SP_ADD = 6 };
+enum { SP_PLAIN = 0, SP_CG = 1, SP_RESNORM = 2, SP_RES = 3, SP_JACOBI = 4, SP_JACOBI_DOT = 5, SP_ADD = 6,
+       SP_RES0 = 7 /* stencil form only: Y = B - A (omega D^-1 B), the residual after the zero-guess Jacobi sweep */ };
 
 template <typename T> struct CsrDev {
   const int* rowptr;
@@ -975,20 +976,28 @@ k_stencil(const DiaDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const S
 #pragma unroll
       for (int s = 0; s < 9; ++s) v[s] = __ldcs(A.vals + (size_t)s * A.ld + row);   // streamed once: evict first
       T xv[9][CPT];
+      T wj[9];
 #pragma unroll
       for (int s = 0; s < 9; ++s) {
         // missing neighbours carry a zero value: any in-range row will do for the gather
         int j = row + (s / 3 - 1) * nr + (s % 3 - 1);
         j = max(0, min(n - 1, j));
-        ldvec<T, CPT>(X + (size_t)j * KT + c0, xv[s]);
+        if (MODE == SP_RES0) {       // x_j = omega D^-1_j b_j is never stored: gather b and 1/diag instead
+          ldvec<T, CPT>(ep.B + (size_t)j * KT + c0, xv[s]);
+          wj[s] = ep.omega * ep.dinv[j];
+        } else {
+          ldvec<T, CPT>(X + (size_t)j * KT + c0, xv[s]);
+        }
       }
       T acc[CPT];
 #pragma unroll
       for (int i = 0; i < CPT; ++i) acc[i] = T(0);
 #pragma unroll
-      for (int s = 0; s < 9; ++s)
+      for (int s = 0; s < 9; ++s) {
+        const T vs = MODE == SP_RES0 ? v[s] * wj[s] : v[s];
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) acc[i] += v[s] * xv[s][i];
+        for (int i = 0; i < CPT; ++i) acc[i] += vs * xv[s][i];
+      }
       const size_t o = (size_t)row * KT + c0;
       T out[CPT], bb[CPT];
       constexpr bool NEEDB = (MODE == SP_RESNORM || MODE == SP_RES || MODE == SP_JACOBI || MODE == SP_JACOBI_DOT);
@@ -1010,6 +1019,8 @@ k_stencil(const DiaDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const S
           dot1[i] += (double)bb[i] * (double)bb[i];
         } else if (MODE == SP_RES) {
           out[i] = bb[i] - acc[i];
+        } else if (MODE == SP_RES0) {
+          out[i] = xo - acc[i];                    // xv[4] holds the row's own b
         } else {
           const T yn = xo + dv * (bb[i] - acc[i]);
           out[i] = yn;
@@ -1126,7 +1137,14 @@ k_stencil_prolong_jacobi(const DiaDev<T> A, const CsrP<T> P, const T* __restrict
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int g = (it0 + u * NT) % CG;
-          ldvec<T, CPT>(X0 + (size_t)rowu[u] * KT + g * CPT, x1[u]);
+          if (X0) {
+            ldvec<T, CPT>(X0 + (size_t)rowu[u] * KT + g * CPT, x1[u]);
+          } else {                       // x0 = omega D^-1 b, never stored
+            ldvec<T, CPT>(ep.B + (size_t)rowu[u] * KT + g * CPT, x1[u]);
+            const T w0 = ep.omega * ep.dinv[rowu[u]];
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) x1[u][i] *= w0;
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             cj[u][q] = __ldg(P.ell_col + (size_t)q * P.ell_ld + rowu[u]);
@@ -1166,7 +1184,14 @@ k_stencil_prolong_jacobi(const DiaDev<T> A, const CsrP<T> P, const T* __restrict
       if (c >= 0 && c < ncol && r >= 0 && r < nr && row_l < n) {
         const int row = (int)row_l;
         const int a = P.rowptr[row], b = P.rowptr[row + 1];
-        ldvec<T, CPT>(X0 + (size_t)row * KT + g * CPT, x1);
+        if (X0) {
+          ldvec<T, CPT>(X0 + (size_t)row * KT + g * CPT, x1);
+        } else {
+          ldvec<T, CPT>(ep.B + (size_t)row * KT + g * CPT, x1);
+          const T w0 = ep.omega * ep.dinv[row];
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) x1[i] *= w0;
+        }
         int cj[4];
         T pv[4];
 #pragma unroll
@@ -1459,7 +1484,7 @@ k_cg_update_r0(size_t nelem, const T* __restrict__ AP, const T* __restrict__ din
       r32[i] = (TV)r[i];
     }
     vstore(R + e, r);
-    stvec<TV, VEC>(X0 + e, x0);
+    if (X0) stvec<TV, VEC>(X0 + e, x0);        // null: the level-0 kernels form omega D^-1 r on the fly
     if (R32) stvec<TV, VEC>(R32 + e, r32);
   }
 }
