@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--cols", type=int, default=0)
     ap.add_argument("--pairs", type=int, default=0, help="total pairs (strong) / pairs per GPU (weak)")
     ap.add_argument("--scaling", default="", choices=["", "strong", "weak"])
-    ap.add_argument("--bs", type=int, default=16, help="columns per solve_linear_system call in the e2e leg")
+    ap.add_argument("--bs", type=int, default=32, help="columns per solve_linear_system call in the e2e leg")
     ap.add_argument("--precision", default="double")
     ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"])
     ap.add_argument("--rtol", type=float, default=1e-6)

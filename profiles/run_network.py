@@ -42,11 +42,25 @@ def main():
     t_gen = time.time() - t0
     solver = cb.CUDASolver(device=local, precond=args.precond)
     t0 = time.time()
+    comm = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        nn, nnz, rp, ci, va = D.broadcast_csr(L, dist, f"cuda:{local}")
-        factor = D.factor_from_device(nn, nnz, rp, ci, va, solver)
+        dev = torch.device(f"cuda:{local}")
+        dist.init_process_group("nccl", device_id=dev)
+
+        def exchange(raw):
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if raw is not None:
+                t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, src=0)
+            return bytes(t.cpu().tolist())
+        comm = D.Comm(local, rank, world, exchange)          # NCCL behind the C ABI (cs_b200_comm_*)
+        meta = torch.zeros(2, dtype=torch.int64, device=dev)
+        if rank == 0:
+            meta = torch.tensor([L.shape[0], L.nnz], dtype=torch.int64, device=dev)
+        dist.broadcast(meta, src=0)
+        t0 = time.time()
+        factor = comm.create_factor(L, solver, shape=(int(meta[0]), int(meta[1])))   # cs_b200_create_bcast
     else:
         factor = cb.construct_cholesky_factor(L, solver)
     t_setup = time.time() - t0
@@ -62,6 +76,8 @@ def main():
         V, iters, relres, cols = core.all_to_one_batched(factor, focal, shard=(rank, world),
                                                          device_resident=args.device_resident,
                                                          accumulate=args.device_resident)
+        if comm is not None and args.device_resident:
+            comm.reduce_currents(factor)                     # end of the job: SUM / MAX of the current vectors
         torch.cuda.synchronize()
         dt = torch.tensor([time.time() - t0], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
@@ -96,6 +112,7 @@ def main():
         print(json.dumps(out))
     factor.close()
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 
