@@ -1254,7 +1254,9 @@ int gather_panel_status(cs_b200_handle* h, int kt, int64_t c0, int64_t* iters, d
       }
       *any_fail = true;
     }
-    if (ct.iters[c] >= itmax && std::sqrt(ct.rho[c]) > ct.tol[c]) *any_maxit = true;
+    // a column frozen by the stagnation guard above its tolerance is reported like one that ran into
+    // itmax: results written, CS_B200_ERR_MAXITER, the true-residual gate decides (core.jl:639-641)
+    if ((ct.iters[c] >= itmax || ct.stalled[c]) && std::sqrt(ct.rho[c]) > ct.tol[c]) *any_maxit = true;
   }
   return 0;
 }
@@ -1606,7 +1608,7 @@ int solve_pairs_t(cs_b200_handle* h, int64_t k, const int64_t* src, const int64_
     c0 += kt;
   }
   if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
-  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
+  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached (or the recurrence stagnated) before rtol");
   return CS_B200_OK;
 }
 
@@ -1639,7 +1641,7 @@ int solve_sources_t(cs_b200_handle* h, int64_t k, const int64_t* colptr, const i
     c0 += kt;
   }
   if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
-  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
+  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached (or the recurrence stagnated) before rtol");
   return CS_B200_OK;
 }
 
@@ -1682,7 +1684,7 @@ int solve_pairs_superposed_t(cs_b200_handle* h, int64_t np, const int64_t* nodes
   cleanup();
   if (rc) return rc;
   if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
-  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
+  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached (or the recurrence stagnated) before rtol");
   return CS_B200_OK;
 }
 
@@ -1717,7 +1719,7 @@ int solve_rhs_t(cs_b200_handle* h, int64_t k, const T* rhs, T* lhs, double rtol,
   cudaStreamSynchronize(h->stream);
   if (rc) return rc;
   if (any_fail) return set_err(h, CS_B200_ERR_RESIDUAL, "%s", msg.c_str());
-  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached before rtol");
+  if (any_maxit) return set_err(h, CS_B200_ERR_MAXITER, "itmax reached (or the recurrence stagnated) before rtol");
   return CS_B200_OK;
 }
 

@@ -45,7 +45,8 @@ enum cs_b200_status {
   CS_B200_ERR_RESIDUAL = -3,   /* a column failed the true-residual gate (1e-4), the
                                   reference's `error("... exceeds tolerance 1e-4")`,
                                   src/core.jl:641,650                              */
-  CS_B200_ERR_MAXITER = -4,    /* itmax reached before rtol (results still written) */
+  CS_B200_ERR_MAXITER = -4,    /* itmax reached, or a column's recurrence stagnated (reduced-precision
+                                  storage), before rtol: results still written, relres[] says how far */
   CS_B200_ERR_UNSUPPORTED = -5
 };
 

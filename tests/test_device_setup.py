@@ -79,7 +79,7 @@ def test_device_setup_same_iterations_and_resistances(mixed):
 @pytest.mark.parametrize("shape", [(3, 3), (9, 40), (128, 1), (1, 700), (141, 143), (400, 90)])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_windows_built_on_device_spmm(shape, dtype):
-    """Row blocks (pointer doubling) + window records packed on the device, every panel width,
+    """Row blocks (chunk-local greedy walk) + window records packed on the device, every panel width,
     ragged holes, tiny and degenerate rasters."""
     A = holey(*shape, seed=shape[0] + shape[1], holes=0.12) if min(shape) > 1 else \
         graph.synthetic_raster_laplacian(*shape, seed=2)[0].tocsr()
