@@ -798,6 +798,13 @@ CsrDev<T> view(const DevCsr& m) {
   return CsrDev<T>{m.rowptr, m.colidx, (const T*)m.vals, m.bstart, m.nblocks, m.nrows};
 }
 
+// experimental variants of the stencil kernel (kernels.cuh): 0 = nine gathers per row, 1 = sliding
+// 3 x 3 register window, 2 = sliding window + L2 prefetch two columns ahead
+static int stencil_variant() {
+  static const int v = [] { const char* e = std::getenv("CS_B200_STENCIL_VARIANT"); return e ? std::atoi(e) : 0; }();
+  return v;
+}
+
 // Y = op(M X) with the fused epilogue MODE (kernels.cuh).  `timed`: counts as a launch of
 // the dominant kernel for the per-launch profile (finest-level operator only).
 template <typename T, int KT, int MODE>
@@ -834,7 +841,11 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
       const long long ntiles = (long long)((m.dia_nr + rpp - 1) / rpp) *
                                ((((long long)m.nrows + m.dia_nr - 1) / m.dia_nr + ST_TC - 1) / ST_TC);
       const int sg = (int)std::max<long long>(1, std::min<long long>(h->grid_spmm, ntiles));
-      k_stencil<T, KT, MODE><<<sg, NT, 0, h->stream>>>(a, X, Y, ep);
+      switch (stencil_variant()) {
+        case 1: k_stencil<T, KT, MODE, true><<<sg, NT, 0, h->stream>>>(a, X, Y, ep); break;
+        case 2: k_stencil<T, KT, MODE, true, 2><<<sg, NT, 0, h->stream>>>(a, X, Y, ep); break;
+        default: k_stencil<T, KT, MODE><<<sg, NT, 0, h->stream>>>(a, X, Y, ep);
+      }
     }
   } else if (m.win_meta) {
     const WinCsr<T> w{m.win_meta, m.blob, m.has_dinv, m.rowptr, m.colidx, (const T*)m.vals, m.win_nblocks};
@@ -938,7 +949,11 @@ void launch_stencil_res0(cs_b200_handle* h, DevLevel& L, const T* B, T* Tout, bo
     h->prof_pair_bytes.push_back(fb);
     cudaEventRecord(e0, h->stream);
   }
-  k_stencil<T, KT, SP_RES0><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep);
+  switch (stencil_variant()) {
+    case 1: k_stencil<T, KT, SP_RES0, true><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep); break;
+    case 2: k_stencil<T, KT, SP_RES0, true, 2><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep); break;
+    default: k_stencil<T, KT, SP_RES0><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep);
+  }
   if (prof) cudaEventRecord(e1, h->stream);
   h->stats.kernel_launches++;
   if (timed) h->stats.spmm_launches++;
@@ -977,7 +992,9 @@ void launch_prolong_jacobi(cs_b200_handle* h, DevLevel& L, const T* Yc, const T*
     h->prof_pair_bytes.push_back(fb);
     cudaEventRecord(e0, h->stream);
   }
-  k_stencil_prolong_jacobi<T, KT, MODE><<<grid, NT, SMEM, h->stream>>>(a, p, Yc, X0, Yout, ep);
+  static const bool occ4 = [] { const char* e = std::getenv("CS_B200_PJ_OCC4"); return e && e[0] == '1'; }();
+  if (occ4) k_stencil_prolong_jacobi<T, KT, MODE, 4><<<grid, NT, SMEM, h->stream>>>(a, p, Yc, X0, Yout, ep);
+  else k_stencil_prolong_jacobi<T, KT, MODE><<<grid, NT, SMEM, h->stream>>>(a, p, Yc, X0, Yout, ep);
   if (prof) cudaEventRecord(e1, h->stream);
   h->stats.kernel_launches++;
   if (timed) h->stats.spmm_launches++;
