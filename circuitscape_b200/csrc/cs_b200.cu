@@ -798,10 +798,9 @@ CsrDev<T> view(const DevCsr& m) {
   return CsrDev<T>{m.rowptr, m.colidx, (const T*)m.vals, m.bstart, m.nblocks, m.nrows};
 }
 
-// experimental variants of the stencil kernel (kernels.cuh): 0 = nine gathers per row, 1 = sliding
-// 3 x 3 register window, 2 = sliding window + L2 prefetch two columns ahead
-static int stencil_variant() {
-  static const int v = [] { const char* e = std::getenv("CS_B200_STENCIL_VARIANT"); return e ? std::atoi(e) : 0; }();
+// A/B switch: CS_B200_STENCIL_OCC4=1 holds the stencil kernel to 64 registers (4 CTAs per SM)
+static bool stencil_occ4() {
+  static const bool v = [] { const char* e = std::getenv("CS_B200_STENCIL_OCC4"); return e && e[0] == '1'; }();
   return v;
 }
 
@@ -841,11 +840,8 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
       const long long ntiles = (long long)((m.dia_nr + rpp - 1) / rpp) *
                                ((((long long)m.nrows + m.dia_nr - 1) / m.dia_nr + ST_TC - 1) / ST_TC);
       const int sg = (int)std::max<long long>(1, std::min<long long>(h->grid_spmm, ntiles));
-      switch (stencil_variant()) {
-        case 1: k_stencil<T, KT, MODE, true><<<sg, NT, 0, h->stream>>>(a, X, Y, ep); break;
-        case 2: k_stencil<T, KT, MODE, true, 2><<<sg, NT, 0, h->stream>>>(a, X, Y, ep); break;
-        default: k_stencil<T, KT, MODE><<<sg, NT, 0, h->stream>>>(a, X, Y, ep);
-      }
+      if (stencil_occ4()) k_stencil<T, KT, MODE, 4><<<sg, NT, 0, h->stream>>>(a, X, Y, ep);
+      else k_stencil<T, KT, MODE><<<sg, NT, 0, h->stream>>>(a, X, Y, ep);
     }
   } else if (m.win_meta) {
     const WinCsr<T> w{m.win_meta, m.blob, m.has_dinv, m.rowptr, m.colidx, (const T*)m.vals, m.win_nblocks};
@@ -949,11 +945,8 @@ void launch_stencil_res0(cs_b200_handle* h, DevLevel& L, const T* B, T* Tout, bo
     h->prof_pair_bytes.push_back(fb);
     cudaEventRecord(e0, h->stream);
   }
-  switch (stencil_variant()) {
-    case 1: k_stencil<T, KT, SP_RES0, true><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep); break;
-    case 2: k_stencil<T, KT, SP_RES0, true, 2><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep); break;
-    default: k_stencil<T, KT, SP_RES0><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep);
-  }
+  if (stencil_occ4()) k_stencil<T, KT, SP_RES0, 4><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep);
+  else k_stencil<T, KT, SP_RES0><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep);
   if (prof) cudaEventRecord(e1, h->stream);
   h->stats.kernel_launches++;
   if (timed) h->stats.spmm_launches++;
@@ -992,9 +985,8 @@ void launch_prolong_jacobi(cs_b200_handle* h, DevLevel& L, const T* Yc, const T*
     h->prof_pair_bytes.push_back(fb);
     cudaEventRecord(e0, h->stream);
   }
-  static const bool occ4 = [] { const char* e = std::getenv("CS_B200_PJ_OCC4"); return e && e[0] == '1'; }();
-  if (occ4) k_stencil_prolong_jacobi<T, KT, MODE, 4><<<grid, NT, SMEM, h->stream>>>(a, p, Yc, X0, Yout, ep);
-  else k_stencil_prolong_jacobi<T, KT, MODE><<<grid, NT, SMEM, h->stream>>>(a, p, Yc, X0, Yout, ep);
+  constexpr int MINB = sizeof(T) == 4 ? 4 : 3;
+  k_stencil_prolong_jacobi<T, KT, MODE, MINB><<<grid, NT, SMEM, h->stream>>>(a, p, Yc, X0, Yout, ep);
   if (prof) cudaEventRecord(e1, h->stream);
   h->stats.kernel_launches++;
   if (timed) h->stats.spmm_launches++;

@@ -945,12 +945,9 @@ template <typename T> struct DiaDev {
 
 constexpr int ST_TC = 16;   // raster columns per tile
 
-// SLIDE: the thread keeps the 3 x 3 window of panel vectors in registers while it sweeps the tile's
-// columns and gathers only the 3 vectors of the incoming strip per row (instead of all 9): a third of the
-// L1 traffic of the gathers, same DRAM traffic, same arithmetic in the same order.
-// PF > 0 (with SLIDE): L2 prefetch hints for the operands of column c + PF (one lane per 32-byte sector).
-template <typename T, int KT, int MODE, bool SLIDE = false, int PF = 0>
-__global__ void __launch_bounds__(NT, 3)
+// MINB: resident CTAs per SM the register allocation is held to (3 -> 80 registers, 4 -> 64).
+template <typename T, int KT, int MODE, int MINB = 3>
+__global__ void __launch_bounds__(NT, MINB)
 k_stencil(const DiaDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
   constexpr int V16 = 16 / (int)sizeof(T);
   constexpr int CPT = KT < V16 ? KT : V16;      // panel columns per thread (one 16-byte vector)
@@ -972,112 +969,6 @@ k_stencil(const DiaDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const S
     const int r = rc * RPP + rl;                // row within the raster column
     if (r >= nr) continue;
     const int cend = min(ncol, (tc + 1) * ST_TC);
-    if constexpr (SLIDE) {
-      // strips: [row offset -1, 0, +1][panel columns of this thread] of raster columns c-1, c, c+1
-      T S0[3][CPT], S1[3][CPT], S2[3][CPT];
-      T W0[3], W1[3], W2[3];                       // SP_RES0: omega / diag of the strip's rows
-      auto load_strip = [&](int cs, T (&d)[3][CPT], T (&w)[3]) {
-        const long long base = (long long)cs * nr + r - 1;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const long long jl = base + q;
-          const int j = (int)(jl < 0 ? 0 : (jl > (long long)n - 1 ? (long long)n - 1 : jl));
-          if (MODE == SP_RES0) {
-            ldvec<T, CPT>(ep.B + (size_t)j * KT + c0, d[q]);
-            w[q] = ep.omega * ep.dinv[j];
-          } else {
-            ldvec<T, CPT>(X + (size_t)j * KT + c0, d[q]);
-            w[q] = T(1);
-          }
-        }
-      };
-      auto body = [&](int c, T (&L)[3][CPT], T (&C)[3][CPT], T (&R)[3][CPT], T (&WL)[3], T (&WC)[3], T (&WR)[3]) -> bool {
-        const long long row_l = (long long)c * nr + r;
-        if (row_l >= n) return false;
-        const int row = (int)row_l;
-        T v[9];
-#pragma unroll
-        for (int s = 0; s < 9; ++s) v[s] = __ldcs(A.vals + (size_t)s * A.ld + row);
-        load_strip(c + 1, R, WR);
-        if constexpr (PF > 0) {
-          const long long rp = row_l + (long long)PF * nr;
-          if (c + PF < cend && rp < n) {
-            constexpr int SECT = 32 / (int)sizeof(T);
-            if (cg == 0 && (rl & (SECT - 1)) == 0) {
-#pragma unroll
-              for (int s = 0; s < 9; ++s)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vals + (size_t)s * A.ld + (size_t)rp));
-            }
-            const long long xp = rp + nr;                 // the strip that column needs first
-            if ((cg & 1) == 0 && xp < n)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"((MODE == SP_RES0 ? ep.B : X) + (size_t)xp * KT + c0));
-          }
-        }
-        T acc[CPT];
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) acc[i] = T(0);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const T vl = MODE == SP_RES0 ? v[q] * WL[q] : v[q];
-#pragma unroll
-          for (int i = 0; i < CPT; ++i) acc[i] += vl * L[q][i];
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const T vc = MODE == SP_RES0 ? v[3 + q] * WC[q] : v[3 + q];
-#pragma unroll
-          for (int i = 0; i < CPT; ++i) acc[i] += vc * C[q][i];
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const T vr = MODE == SP_RES0 ? v[6 + q] * WR[q] : v[6 + q];
-#pragma unroll
-          for (int i = 0; i < CPT; ++i) acc[i] += vr * R[q][i];
-        }
-        const size_t o = (size_t)row * KT + c0;
-        T out[CPT], bb[CPT];
-        constexpr bool NEEDB = (MODE == SP_RESNORM || MODE == SP_RES || MODE == SP_JACOBI || MODE == SP_JACOBI_DOT);
-        if (NEEDB) ldvec<T, CPT>(ep.B + o, bb);
-        T dv = T(0);
-        if (MODE == SP_JACOBI || MODE == SP_JACOBI_DOT) dv = ep.omega * ep.dinv[row];
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-          const T xo = C[1][i];
-          if (MODE == SP_PLAIN) {
-            out[i] = acc[i];
-          } else if (MODE == SP_CG) {
-            out[i] = acc[i];
-            dot0[i] += (double)acc[i] * (double)xo;
-          } else if (MODE == SP_RESNORM) {
-            const T rr = bb[i] - acc[i];
-            out[i] = rr;
-            dot0[i] += (double)rr * (double)rr;
-            dot1[i] += (double)bb[i] * (double)bb[i];
-          } else if (MODE == SP_RES) {
-            out[i] = bb[i] - acc[i];
-          } else if (MODE == SP_RES0) {
-            out[i] = xo - acc[i];
-          } else {
-            const T yn = xo + dv * (bb[i] - acc[i]);
-            out[i] = yn;
-            if (MODE == SP_JACOBI_DOT) dot0[i] += (double)bb[i] * (double)yn;
-          }
-        }
-        stvec<T, CPT>(Y + o, out);
-        return true;
-      };
-      int c = tc * ST_TC;
-      load_strip(c - 1, S0, W0);
-      load_strip(c, S1, W1);
-      while (true) {
-        if (c >= cend || !body(c, S0, S1, S2, W0, W1, W2)) break;
-        ++c;
-        if (c >= cend || !body(c, S1, S2, S0, W1, W2, W0)) break;
-        ++c;
-        if (c >= cend || !body(c, S2, S0, S1, W2, W0, W1)) break;
-        ++c;
-      }
-    } else
     for (int c = tc * ST_TC; c < cend; ++c) {
       const long long row_l = (long long)c * nr + r;
       if (row_l >= n) break;
@@ -1196,13 +1087,14 @@ template <typename T> struct CsrP {
   size_t ell_ld;
 };
 
-// MINB = 4: four CTAs per SM (64 registers); the b.z partial sums of a thread are then kept in T (the
-// V-cycle's precision) instead of double, which is what frees the registers -- ~70 products per thread,
-// folded into the double tree reduction afterwards.
+// MINB = 4 (the fp32 V-cycle): four CTAs per SM, 64 registers.  The kernel is latency-bound, and the
+// fourth CTA bought 19 % (0.497 -> 0.405 ms at 3163^2, k = 8).  What frees the registers: a thread keeps
+// its b.z partial sums (~70 products) in T, the V-cycle's own precision, instead of double; they enter the
+// double tree reduction afterwards.  MINB = 3 keeps double partial sums (fp64 cycles).
 template <typename T, int MINB> struct PjDot { typedef double type; };
 template <typename T> struct PjDot<T, 4> { typedef T type; };
 
-template <typename T, int KT, int MODE, int MINB = 1>
+template <typename T, int KT, int MODE, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_stencil_prolong_jacobi(const DiaDev<T> A, const CsrP<T> P, const T* __restrict__ Yc, const T* __restrict__ X0,
                          T* __restrict__ Z, const SpmmEpi<T> ep) {
