@@ -798,12 +798,6 @@ CsrDev<T> view(const DevCsr& m) {
   return CsrDev<T>{m.rowptr, m.colidx, (const T*)m.vals, m.bstart, m.nblocks, m.nrows};
 }
 
-// A/B switch: CS_B200_STENCIL_OCC4=1 holds the stencil kernel to 64 registers (4 CTAs per SM)
-static bool stencil_occ4() {
-  static const bool v = [] { const char* e = std::getenv("CS_B200_STENCIL_OCC4"); return e && e[0] == '1'; }();
-  return v;
-}
-
 // Y = op(M X) with the fused epilogue MODE (kernels.cuh).  `timed`: counts as a launch of
 // the dominant kernel for the per-launch profile (finest-level operator only).
 template <typename T, int KT, int MODE>
@@ -840,8 +834,7 @@ void launch_spmm_on(cs_b200_handle* h, const DevCsr& m, const T* X, T* Y, const 
       const long long ntiles = (long long)((m.dia_nr + rpp - 1) / rpp) *
                                ((((long long)m.nrows + m.dia_nr - 1) / m.dia_nr + ST_TC - 1) / ST_TC);
       const int sg = (int)std::max<long long>(1, std::min<long long>(h->grid_spmm, ntiles));
-      if (stencil_occ4()) k_stencil<T, KT, MODE, 4><<<sg, NT, 0, h->stream>>>(a, X, Y, ep);
-      else k_stencil<T, KT, MODE><<<sg, NT, 0, h->stream>>>(a, X, Y, ep);
+      k_stencil<T, KT, MODE><<<sg, NT, 0, h->stream>>>(a, X, Y, ep);
     }
   } else if (m.win_meta) {
     const WinCsr<T> w{m.win_meta, m.blob, m.has_dinv, m.rowptr, m.colidx, (const T*)m.vals, m.win_nblocks};
@@ -945,8 +938,7 @@ void launch_stencil_res0(cs_b200_handle* h, DevLevel& L, const T* B, T* Tout, bo
     h->prof_pair_bytes.push_back(fb);
     cudaEventRecord(e0, h->stream);
   }
-  if (stencil_occ4()) k_stencil<T, KT, SP_RES0, 4><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep);
-  else k_stencil<T, KT, SP_RES0><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep);
+  k_stencil<T, KT, SP_RES0><<<sg, NT, 0, h->stream>>>(a, nullptr, Tout, ep);
   if (prof) cudaEventRecord(e1, h->stream);
   h->stats.kernel_launches++;
   if (timed) h->stats.spmm_launches++;

@@ -945,9 +945,12 @@ template <typename T> struct DiaDev {
 
 constexpr int ST_TC = 16;   // raster columns per tile
 
-// MINB: resident CTAs per SM the register allocation is held to (3 -> 80 registers, 4 -> 64).
-template <typename T, int KT, int MODE, int MINB = 3>
-__global__ void __launch_bounds__(NT, MINB)
+// Three CTAs per SM (80 registers, all 18 loads of a row in flight).  Holding it to 64 registers for a
+// fourth CTA compiles without spills but measured 3 % slower on the CG and residual epilogues (the loads
+// are issued in two batches); a sliding 3 x 3 register window (3 gathers per row instead of 9) measured
+// 25 % slower at k = 8 -- profiles/README.md, "kernel variants".
+template <typename T, int KT, int MODE>
+__global__ void __launch_bounds__(NT, 3)
 k_stencil(const DiaDev<T> A, const T* __restrict__ X, T* __restrict__ Y, const SpmmEpi<T> ep) {
   constexpr int V16 = 16 / (int)sizeof(T);
   constexpr int CPT = KT < V16 ? KT : V16;      // panel columns per thread (one 16-byte vector)
