@@ -156,3 +156,100 @@ def test_streaming_sink_writes_the_same_files_from_device_results(golden, tmp_pa
         ga, _ = read_asc(os.path.join(pa, f))
         gb, _ = read_asc(os.path.join(pb, f))
         assert np.array_equal(ga, gb), f
+
+
+# ---- GeoTIFF output (cfg.write_as_tif, src/out.jl:338,378,483-531) ---------------------------------
+def read_tif(path):
+    """Minimal little-endian classic-TIFF reader for what `write_tif` emits: returns (array, tags)."""
+    import struct
+    import zlib
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"II*\x00"
+    (ifd,) = struct.unpack_from("<I", raw, 4)
+    (cnt,) = struct.unpack_from("<H", raw, ifd)
+    size = {2: 1, 3: 2, 4: 4, 12: 8}
+    code = {3: "H", 4: "I", 12: "d"}
+    tags, prev = {}, 0
+    for i in range(cnt):
+        tag, typ, n = struct.unpack_from("<HHI", raw, ifd + 2 + 12 * i)
+        assert tag > prev            # TIFF 6.0: entries sorted by tag
+        prev = tag
+        at = ifd + 2 + 12 * i + 8
+        if n * size[typ] > 4:
+            (at,) = struct.unpack_from("<I", raw, at)
+            assert at % 2 == 0       # values start on a word boundary
+        tags[tag] = raw[at:at + n] if typ == 2 else list(struct.unpack_from("<" + code[typ] * n, raw, at))
+    assert struct.unpack_from("<I", raw, ifd + 2 + 12 * cnt)[0] == 0     # single IFD
+    ncols, nrows, bps = tags[256][0], tags[257][0], tags[258][0]
+    assert tags[339] == [3] and tags[277] == [1] and tags[262] == [1]
+    parts = []
+    for off, nb in zip(tags[273], tags[279]):
+        b = raw[off:off + nb]
+        parts.append(zlib.decompress(b) if tags[259] == [8] else b)
+    a = np.frombuffer(b"".join(parts), dtype="<f8" if bps == 64 else "<f4").reshape(nrows, ncols)
+    return a, tags
+
+
+@pytest.mark.parametrize("compress", ["deflate", "none"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_write_tif_round_trip(tmp_path, compress, dtype):
+    rng = np.random.default_rng(7)
+    a = rng.random((37, 53)).astype(dtype)
+    a[3, 4] = -9999.0
+    wkt = 'PROJCS["NAD83 / UTM zone 10N",GEOGCS["NAD83",DATUM["North_American_Datum_1983"]]]'
+    m = O.RasterMeta(ncols=53, nrows=37, xllcorner=100.5, yllcorner=-20.0, cellsize=0.25, wkt=wkt)
+    p = O.write_tif(str(tmp_path / "t.tif"), a, m, compress=compress, rows_per_strip=5)
+    b, tags = read_tif(p)
+    assert b.dtype == np.dtype(dtype) and np.array_equal(b, a)           # lossless
+    assert len(tags[273]) == 8 and tags[278] == [5]
+    assert tags[33550] == [0.25, 0.25, 0.0]                              # ModelPixelScale
+    assert tags[33922] == [0.0, 0.0, 0.0, 100.5, -20.0 + 37 * 0.25, 0.0]  # tiepoint: upper-left corner
+    assert tags[42113].rstrip(b"\0") == b"-9999"                         # GDAL_NODATA
+    keys = tags[34735]
+    assert keys[:4] == [1, 1, 0, 4] and keys[4:8] == [1024, 0, 1, 1] and keys[12:16] == [3072, 0, 1, 32767]
+    assert keys[16:18] == [3073, 34737] and keys[19] == 0
+    cit = tags[34737][keys[19]:keys[19] + keys[18]]
+    assert cit == ("ESRI PE String = " + wkt + "|").encode()
+
+
+def test_write_tif_rotated_transform_and_no_projection(tmp_path):
+    a = np.arange(12, dtype=np.float64).reshape(3, 4)
+    m = O.RasterMeta(ncols=4, nrows=3, transform=(10.0, 2.0, 0.5, 50.0, -0.25, -2.0))
+    b, tags = read_tif(O.write_tif(str(tmp_path / "r.tif"), a, m))
+    assert np.array_equal(b, a)
+    assert 33550 not in tags and 33922 not in tags
+    assert tags[34264] == [2.0, 0.5, 0.0, 10.0, -0.25, -2.0, 0.0, 50.0, 0, 0, 0, 0, 0, 0, 0, 1.0]
+    assert tags[34735] == [1, 1, 0, 1, 1025, 0, 1, 1] and 34737 not in tags
+    with pytest.raises(ValueError):
+        O.write_tif(str(tmp_path / "bad.tif"), a, O.RasterMeta(ncols=5, nrows=3))
+    with pytest.raises(ValueError):
+        O.write_tif(str(tmp_path / "bad.tif"), a, m, compress="lzw")
+
+
+def test_write_tif_is_readable_by_an_independent_decoder(tmp_path):
+    Image = pytest.importorskip("PIL.Image")
+    a = np.random.default_rng(1).random((40, 31)).astype(np.float32)
+    m = O.RasterMeta(ncols=31, nrows=40, cellsize=30.0)
+    for compress in ("deflate", "none"):
+        p = O.write_tif(str(tmp_path / f"{compress}.tif"), a, m, compress=compress)
+        with Image.open(p) as im:
+            assert im.size == (31, 40) and im.mode == "F"
+            assert np.array_equal(np.array(im), a)
+            assert im.tag_v2[33550] == (30.0, 30.0, 0.0)
+
+
+def test_pairwise_outputs_as_tif(golden, tmp_path):
+    r, _ = cases.run_raster_pairwise(golden, "sgVerify1", cb.CUDASolver())
+    _, inp, _ = co.load_case(golden, "sgVerify1")
+    shape = inp["habitat_file"][1].shape
+    meta = O.RasterMeta(ncols=shape[1], nrows=shape[0], xllcorner=3.5, yllcorner=-2.0, cellsize=0.25)
+    asc = O.write_pairwise_outputs(r, str(tmp_path / "a" / "x.out"), meta)
+    tif = O.write_pairwise_outputs(r, str(tmp_path / "t" / "x.out"), meta, write_as_tif=True)
+    assert [os.path.basename(p).replace(".tif", ".asc") for p in tif] == [os.path.basename(p) for p in asc]
+    n = 0
+    for pa, pt in zip(asc, tif):
+        if pa.endswith(".asc"):
+            assert pt.endswith(".tif")
+            assert np.array_equal(read_tif(pt)[0], read_asc(pa)[0])       # same pixels in both formats
+            n += 1
+    assert n >= 2
